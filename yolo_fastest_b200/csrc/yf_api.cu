@@ -1,0 +1,810 @@
+// yf_api.cu — C ABI (include/yf.h) of the B200-native YOLO-Fastest hot path: weight packing,
+// the launch plan of fused groups, and the entry points. Kernels live in yf_kernels.cuh / yf_post.cuh.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/yf.h"
+#include "yf_kernels.cuh"
+#include "yf_post.cuh"
+
+using namespace yf;
+
+// ---------------------------------------------------------------------------------------------
+// canonical parameter order (= forward order of the reference model, yolo_fastest.py:78-148)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Spec {
+    std::string name;
+    int cin, cout, k, groups;
+    bool deconv;
+    int64_t w_off, b_off;   // offsets (floats) into the host blob
+    int64_t w_count() const { return deconv ? (int64_t)cin * cout * k * k : (int64_t)cout * (cin / groups) * k * k; }
+};
+
+struct SpecTable {
+    std::vector<Spec> specs;
+    std::map<std::string, int> index;
+    int64_t total = 0;
+    void add(const std::string& name, int cin, int cout, int k, int groups = 1, bool deconv = false) {
+        Spec s{name, cin, cout, k, groups, deconv, 0, 0};
+        s.w_off = total;
+        total += s.w_count();
+        s.b_off = total;
+        total += cout;
+        index[name] = (int)specs.size();
+        specs.push_back(s);
+    }
+    void irb(const std::string& name, int io, int mid) {   // BasicResBlock (yolo_fastest.py:52-58)
+        add(name + ".conv1", io, mid, 1);
+        add(name + ".conv2", mid, mid, 3, mid);
+        add(name + ".conv3", mid, io, 1);
+    }
+    const Spec& get(const std::string& name) const { return specs[index.at(name)]; }
+};
+
+SpecTable build_specs(int in_ch, int num_cls, int num_anchors) {
+    SpecTable t;
+    const int nout = num_anchors * (5 + num_cls);
+    t.add("conv0", in_ch, 8, 3);
+    t.add("conv1_2", 8, 8, 1); t.add("conv1_3", 8, 8, 3, 8); t.add("conv1_4", 8, 4, 1);
+    t.irb("res1_1", 4, 8);
+    t.add("conv1_8", 4, 24, 1); t.add("conv1_9", 24, 24, 3); t.add("conv2_1", 24, 8, 1);
+    t.irb("res2_1", 8, 32); t.irb("res2_2", 8, 32);
+    t.add("conv2_2", 8, 32, 1); t.add("conv2_3", 32, 32, 3, 32); t.add("conv3_1", 32, 8, 1);
+    t.irb("res3_1", 8, 48); t.irb("res3_2", 8, 48);
+    t.add("conv3_2", 8, 48, 1); t.add("conv3_3", 48, 48, 3, 48); t.add("conv3_4", 48, 16, 1);
+    t.irb("res3_3", 16, 96); t.irb("res3_4", 16, 96); t.irb("res3_5", 16, 96); t.irb("res3_6", 16, 96);
+    t.add("conv3_5", 16, 96, 1); t.add("conv3_6", 96, 96, 3, 96); t.add("conv4_1", 96, 24, 1);
+    t.irb("res4_1", 24, 136); t.irb("res4_2", 24, 136); t.irb("res4_3", 24, 136); t.irb("res4_4", 24, 136);
+    t.add("conv4_2", 24, 136, 1); t.add("conv4_3", 136, 136, 3, 136); t.add("conv5_1", 136, 48, 1);
+    t.irb("res5_1", 48, 224); t.irb("res5_2", 48, 224); t.irb("res5_3", 48, 224); t.irb("res5_4", 48, 224);
+    t.irb("res5_5", 48, 224);
+    t.add("conv5_2", 48, 96, 1);
+    t.add("conv5_3", 96, 96, 5, 96); t.add("conv5_4", 96, 128, 1);
+    t.add("conv5_5", 128, 128, 5, 128); t.add("conv5_6", 128, 128, 1);
+    t.add("head_5", 128, nout, 1);
+    t.add("deconv5_1", 96, 96, 2, 1, true);
+    t.add("conv4_1_1", 232, 96, 1);
+    t.add("conv4_1_2", 96, 96, 5, 96); t.add("conv4_1_3", 96, 96, 1);
+    t.add("conv4_1_4", 96, 96, 5, 96); t.add("conv4_1_5", 96, 96, 1);
+    t.add("head_4", 96, nout, 1);
+    return t;
+}
+
+thread_local std::string g_err;
+
+void set_err(std::string* dst, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    (dst ? *dst : g_err) = buf;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct GroupArgs {
+    const float* x = nullptr;    // input activation
+    const float* x2 = nullptr;   // second input (upcat: low-res tensor)
+    float* y = nullptr;          // output activation (or head)
+    float* skip = nullptr;       // dual output
+    const float* w = nullptr;    // packed weights (device)
+    int Hin = 0, Win = 0, Hout = 0, Wout = 0;
+    int headn = 0;
+};
+
+struct Group {
+    const char* name;                                   // reference attribute producing the group's output
+    void (*launch)(const GroupArgs&, const void* xin, bool u8in, int B, cudaStream_t);
+    GroupArgs a;
+    int out_ch;                                         // channels of y (0 for heads: written to caller memory)
+    int64_t w_off;                                      // offset into dev blob (floats)
+};
+
+struct yf_ctx {
+    int device = 0, in_ch = 1, num_cls = 3, num_anchors = 3, max_batch = 1, H = 0, W = 0;
+    int nout = 0;
+    bool weights_loaded = false;
+    std::string err;
+    SpecTable specs;
+    std::vector<Group> groups;
+    std::vector<float> host_packed;
+    float* d_w = nullptr;
+    std::vector<float*> d_act;                          // one buffer per group output
+    std::map<std::string, std::pair<float*, int64_t>> taps;   // name -> (buffer, floats per image)
+    float* d_skip = nullptr;                            // conv4_2
+    float* d_hl = nullptr;                              // internal heads for yf_detect
+    float* d_hs = nullptr;
+    float* d_x = nullptr;                               // staging for *_host entry points
+    unsigned char* d_u8 = nullptr;
+    yf_det* d_out = nullptr;
+    int out_cap = 0;                                    // max_det capacity of d_out
+    int32_t* d_counts = nullptr;
+    int32_t* d_status = nullptr;
+    // post-process workspace
+    int NC = 0;
+    yf_det* p_rec = nullptr;
+    double* p_conf = nullptr;
+    int32_t* p_cls = nullptr;
+    int4* p_sbox = nullptr;
+    int32_t* p_order = nullptr;
+    unsigned char* p_alive = nullptr;
+    unsigned char* n_alive = nullptr;                   // yf_nms_sorted_* scratch
+    int n_alive_cap = 0;
+    int64_t launches = 0;
+};
+
+#define CTX_CHECK(ctx)                                         \
+    if (!(ctx)) { set_err(nullptr, "null ctx"); return YF_ERR_ARG; }
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            set_err(&ctx->err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return YF_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// group configurations (tile shapes tuned for the 640x512 / 320x256 maps; any H, W multiple of 32 works)
+//        IrbCfg<CIN, CMID, COUT, KS, S, TH, TW, MC, PN1, PN3, RH, NT, MINB, EXPAND, RES, RELU_OUT, DUAL, HEAD>
+// ---------------------------------------------------------------------------------------------
+using CfgStem = StemCfg<8, 40, 128, 4>;
+using CfgRes1 = IrbCfg<4, 8, 4, 3, 1, 8, 40, 8, 8, 4, 8, 128, 4, true, true, false, false>;
+using CfgDense = DenseCfg<4, 40, 8, 128, 3>;
+using CfgRes2 = IrbCfg<8, 32, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 3, true, true, false, false>;
+using CfgDown2 = IrbCfg<8, 32, 8, 3, 2, 4, 40, 16, 8, 4, 4, 128, 2, true, false, false, false>;
+using CfgRes3a = IrbCfg<8, 48, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 3, true, true, false, false>;
+using CfgWide3 = IrbCfg<8, 48, 16, 3, 1, 8, 40, 16, 8, 8, 8, 128, 3, true, false, false, false>;
+using CfgRes3b = IrbCfg<16, 96, 16, 3, 1, 8, 40, 16, 8, 8, 8, 256, 2, true, true, false, false>;
+using CfgDown3 = IrbCfg<16, 96, 24, 3, 2, 4, 40, 8, 8, 8, 4, 128, 2, true, false, false, false>;
+using CfgRes4 = IrbCfg<24, 136, 24, 3, 1, 8, 40, 16, 8, 8, 8, 256, 2, true, true, false, false>;
+using CfgDown4 = IrbCfg<24, 136, 48, 3, 2, 4, 20, 16, 8, 8, 4, 128, 2, true, false, true, true>;
+using CfgRes5 = IrbCfg<48, 224, 48, 3, 1, 8, 20, 16, 8, 8, 8, 128, 2, true, true, false, false>;
+using CfgPw52 = PwCfg<48, 96, 80, 8, 256, true>;
+using CfgNeckS1 = IrbCfg<96, 96, 128, 5, 1, 8, 20, 32, 4, 8, 4, 320, 1, false, false, false, false>;
+using CfgNeckS2 = IrbCfg<128, 128, 128, 5, 1, 8, 20, 32, 4, 8, 4, 320, 1, false, false, false, false, 1>;
+using CfgUpCat = UpCatCfg<8, 20, 16, 256, 2>;
+using CfgNeckL1 = IrbCfg<96, 96, 96, 5, 1, 8, 20, 32, 4, 8, 4, 256, 2, false, false, false, false>;
+using CfgNeckL2 = IrbCfg<96, 96, 96, 5, 1, 8, 20, 32, 4, 8, 4, 256, 2, false, false, false, false, 1>;
+
+namespace {
+
+template <class C>
+void launch_irb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using G = typename C::G;
+    const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
+    irb_kernel<C><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.skip, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, g.headn);
+}
+template <class C>
+cudaError_t init_irb() { return cudaFuncSetAttribute(irb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
+
+void launch_stem(const GroupArgs& g, const void* xin, bool u8in, int B, cudaStream_t st) {
+    using C = CfgStem;
+    using G = C::G;
+    const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
+    if (u8in) stem_kernel<C, true><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(xin, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty);
+    else stem_kernel<C, false><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(xin, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty);
+}
+void launch_dense(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using C = CfgDense;
+    using G = C::G;
+    const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
+    dense_kernel<C><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty);
+}
+void launch_pw52(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using C = CfgPw52;
+    const int HW = g.Hin * g.Win;
+    const int tiles = cdiv(HW, C::PIXT);
+    pw_kernel<C><<<B * tiles, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, HW, tiles);
+}
+void launch_upcat(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using C = CfgUpCat;
+    const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
+    upcat_kernel<C><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(g.x, g.x2, g.y, g.w, g.Hout, g.Wout, tx, ty);
+}
+
+// ---- packing -------------------------------------------------------------------------------
+struct Folded {
+    const float* blob;
+    const SpecTable* t;
+    const float* w(const std::string& n) const { return blob + t->get(n).w_off; }
+    const float* b(const std::string& n) const { return blob + t->get(n).b_off; }
+};
+
+void pad4(std::vector<float>& v) { while (v.size() % 4) v.push_back(0.f); }
+
+// expand name (or "" when !EXPAND), depthwise name, project name, optional head name
+template <class C>
+int64_t pack_irb(std::vector<float>& out, const Folded& f, const std::string& n1, const std::string& nd,
+                 const std::string& n2, const std::string& nh, int headn) {
+    pad4(out);
+    const int64_t off = (int64_t)out.size();
+    const int headp = rup(headn, 4);
+    out.resize(off + C::OFF_B2 + C::COUT + (C::HEADN > 0 ? C::COUT * headp + headp : 0), 0.f);
+    float* o = out.data() + off;
+    for (int c = 0; c < C::NCHUNK; ++c) {
+        float* cb = o + (int64_t)c * C::CB;
+        for (int ml = 0; ml < C::MC; ++ml) {
+            const int m = c * C::MC + ml;
+            if (m >= C::CMID) continue;   // zero padding of the mid channels
+            if (C::EXPAND) {
+                for (int k = 0; k < C::CIN; ++k) cb[C::OFF_W1 + k * C::MC + ml] = f.w(n1)[m * C::CIN + k];
+                cb[C::OFF_B1 + ml] = f.b(n1)[m];
+            }
+            for (int t = 0; t < C::KK; ++t) cb[C::OFF_WD + ml * C::KK + t] = f.w(nd)[m * C::KK + t];
+            cb[C::OFF_BD + ml] = f.b(nd)[m];
+            for (int n = 0; n < C::COUT; ++n) cb[C::OFF_W2 + ml * C::COUT + n] = f.w(n2)[n * C::CMID + m];
+        }
+    }
+    for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
+    if (C::HEADN > 0) {
+        float* wh = o + C::OFF_B2 + C::COUT;
+        float* bh = wh + C::COUT * headp;
+        for (int k = 0; k < C::COUT; ++k)
+            for (int n = 0; n < headn; ++n) wh[k * headp + n] = f.w(nh)[n * C::COUT + k];
+        for (int n = 0; n < headn; ++n) bh[n] = f.b(nh)[n];
+    }
+    return off;
+}
+
+int64_t pack_stem(std::vector<float>& out, const Folded& f) {
+    using C = CfgStem;
+    pad4(out);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int c = 0; c < 8; ++c)
+        for (int t = 0; t < 9; ++t) o[C::OFF_W0 + t * 8 + c] = f.w("conv0")[c * 9 + t];
+    for (int c = 0; c < 8; ++c) o[C::OFF_B0 + c] = f.b("conv0")[c];
+    for (int m = 0; m < 8; ++m)
+        for (int k = 0; k < 8; ++k) o[C::OFF_W1 + k * 8 + m] = f.w("conv1_2")[m * 8 + k];
+    for (int m = 0; m < 8; ++m) o[C::OFF_B1 + m] = f.b("conv1_2")[m];
+    for (int i = 0; i < 72; ++i) o[C::OFF_WD + i] = f.w("conv1_3")[i];
+    for (int m = 0; m < 8; ++m) o[C::OFF_BD + m] = f.b("conv1_3")[m];
+    for (int n = 0; n < 4; ++n)
+        for (int m = 0; m < 8; ++m) o[C::OFF_W2 + m * 4 + n] = f.w("conv1_4")[n * 8 + m];
+    for (int n = 0; n < 4; ++n) o[C::OFF_B2 + n] = f.b("conv1_4")[n];
+    return off;
+}
+
+int64_t pack_dense(std::vector<float>& out, const Folded& f) {
+    using C = CfgDense;
+    pad4(out);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    const float* w8 = f.w("conv1_8");   // [24][4]
+    const float* w9 = f.w("conv1_9");   // [24][24][3][3]
+    for (int c = 0; c < C::NCHUNK; ++c) {
+        float* cb = o + (int64_t)c * C::CB;
+        for (int ml = 0; ml < C::MC; ++ml) {
+            const int m = c * C::MC + ml;
+            for (int k = 0; k < 4; ++k) cb[C::OFF_W1 + k * C::MC + ml] = w8[m * 4 + k];
+            cb[C::OFF_B1 + ml] = f.b("conv1_8")[m];
+            for (int dy = 0; dy < 3; ++dy)
+                for (int cg = 0; cg < 3; ++cg)
+                    for (int dx = 0; dx < 3; ++dx)
+                        for (int n = 0; n < 8; ++n)
+                            cb[C::OFF_WC + ((ml * 3 + dy) * 3 + cg) * 24 + dx * 8 + n] = w9[(((cg * 8 + n) * 24 + m) * 3 + dy) * 3 + dx];
+        }
+    }
+    for (int n = 0; n < 24; ++n) o[C::OFF_B9 + n] = f.b("conv1_9")[n];
+    for (int n = 0; n < 8; ++n)
+        for (int m = 0; m < 24; ++m) o[C::OFF_W3 + m * 8 + n] = f.w("conv2_1")[n * 24 + m];
+    for (int n = 0; n < 8; ++n) o[C::OFF_B3 + n] = f.b("conv2_1")[n];
+    return off;
+}
+
+int64_t pack_pw52(std::vector<float>& out, const Folded& f) {
+    using C = CfgPw52;
+    pad4(out);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int n = 0; n < C::N; ++n)
+        for (int k = 0; k < C::K; ++k) o[k * C::N + n] = f.w("conv5_2")[n * C::K + k];
+    for (int n = 0; n < C::N; ++n) o[C::K * C::N + n] = f.b("conv5_2")[n];
+    return off;
+}
+
+int64_t pack_upcat(std::vector<float>& out, const Folded& f) {
+    using C = CfgUpCat;
+    pad4(out);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    const float* w = f.w("conv4_1_1");    // [96][232]
+    for (int n = 0; n < 96; ++n) {
+        for (int k = 0; k < 136; ++k) o[C::OFF_WA + k * 96 + n] = w[n * 232 + k];
+        for (int k = 0; k < 96; ++k) o[C::OFF_WB + k * 96 + n] = w[n * 232 + 136 + k];
+        o[C::OFF_B + n] = f.b("conv4_1_1")[n];
+    }
+    const float* wt = f.w("deconv5_1");   // [cin 96][cout 96][2][2]
+    for (int py = 0; py < 2; ++py)
+        for (int c = 0; c < 96; ++c)
+            for (int m = 0; m < 96; ++m)
+                for (int px = 0; px < 2; ++px)
+                    o[C::OFF_WT + ((py * 96 + c) * 96 + m) * 2 + px] = wt[((c * 96 + m) * 2 + py) * 2 + px];
+    for (int m = 0; m < 96; ++m) o[C::OFF_BT + m] = f.b("deconv5_1")[m];
+    return off;
+}
+
+template <class C>
+Group make_irb(const char* name, int out_ch) {
+    Group g{};
+    g.name = name;
+    g.launch = &launch_irb<C>;
+    g.out_ch = out_ch;
+    return g;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------
+extern "C" int yf_abi_version(void) { return YF_ABI_VERSION; }
+
+extern "C" const char* yf_last_error(const yf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int64_t yf_weight_count(int in_ch, int num_cls, int num_anchors) {
+    if (in_ch < 1 || num_cls < 1 || num_anchors < 1) return -1;
+    return build_specs(in_ch, num_cls, num_anchors).total;
+}
+
+static int alloc_all(yf_ctx* ctx) {
+    const int B = ctx->max_batch, H = ctx->H, W = ctx->W;
+    auto dim = [&](int div, int& h, int& w) { h = H / div; w = W / div; };
+    // (name, channels, divisor) of every group output, in launch order
+    struct Out { const char* name; int ch; int div; };
+    const Out outs[] = {
+        {"conv1_4", 4, 2}, {"res1_1", 4, 2}, {"conv2_1", 8, 4}, {"res2_1", 8, 4}, {"res2_2", 8, 4}, {"conv3_1", 8, 8},
+        {"res3_1", 8, 8}, {"res3_2", 8, 8}, {"conv3_4", 16, 8}, {"res3_3", 16, 8}, {"res3_4", 16, 8}, {"res3_5", 16, 8},
+        {"res3_6", 16, 8}, {"conv4_1", 24, 16}, {"res4_1", 24, 16}, {"res4_2", 24, 16}, {"res4_3", 24, 16}, {"res4_4", 24, 16},
+        {"conv5_1", 48, 32}, {"res5_1", 48, 32}, {"res5_2", 48, 32}, {"res5_3", 48, 32}, {"res5_4", 48, 32}, {"res5_5", 48, 32},
+        {"conv5_2", 96, 32}, {"conv5_4", 128, 32}, {"conv4_1_1", 96, 16}, {"conv4_1_3", 96, 16}};
+    for (const Out& o : outs) {
+        int h, w;
+        dim(o.div, h, w);
+        const int64_t per = (int64_t)o.ch * h * w;
+        float* p = nullptr;
+        CU(cudaMalloc(&p, sizeof(float) * per * B));
+        ctx->d_act.push_back(p);
+        ctx->taps[o.name] = {p, per};
+    }
+    {
+        const int64_t per = (int64_t)136 * (H / 16) * (W / 16);
+        CU(cudaMalloc(&ctx->d_skip, sizeof(float) * per * B));
+        ctx->taps["conv4_2"] = {ctx->d_skip, per};
+    }
+    const int64_t hl = (int64_t)ctx->nout * (H / 16) * (W / 16), hs = (int64_t)ctx->nout * (H / 32) * (W / 32);
+    CU(cudaMalloc(&ctx->d_hl, sizeof(float) * hl * B));
+    CU(cudaMalloc(&ctx->d_hs, sizeof(float) * hs * B));
+    CU(cudaMalloc(&ctx->d_x, sizeof(float) * (int64_t)ctx->in_ch * H * W * B));
+    CU(cudaMalloc(&ctx->d_u8, (size_t)ctx->in_ch * H * W * B));
+    CU(cudaMalloc(&ctx->d_counts, sizeof(int32_t) * B));
+    CU(cudaMalloc(&ctx->d_status, sizeof(int32_t) * B));
+    ctx->NC = ctx->num_anchors * ((H / 16) * (W / 16) + (H / 32) * (W / 32));
+    const size_t n = (size_t)ctx->NC * B;
+    CU(cudaMalloc(&ctx->p_rec, sizeof(yf_det) * n));
+    CU(cudaMalloc(&ctx->p_conf, sizeof(double) * n));
+    CU(cudaMalloc(&ctx->p_cls, sizeof(int32_t) * n));
+    CU(cudaMalloc(&ctx->p_sbox, sizeof(int4) * n));
+    CU(cudaMalloc(&ctx->p_order, sizeof(int32_t) * n));
+    CU(cudaMalloc(&ctx->p_alive, n));
+    return YF_OK;
+}
+
+static int ensure_out(yf_ctx* ctx, int max_det) {
+    if (max_det <= ctx->out_cap) return YF_OK;
+    if (ctx->d_out) CU(cudaFree(ctx->d_out));
+    ctx->d_out = nullptr;
+    CU(cudaMalloc(&ctx->d_out, sizeof(yf_det) * (size_t)max_det * ctx->max_batch));
+    ctx->out_cap = max_det;
+    return YF_OK;
+}
+
+static void build_plan(yf_ctx* ctx) {
+    const int H = ctx->H, W = ctx->W;
+    std::vector<Group>& G = ctx->groups;
+    G.clear();
+    int ai = 0;   // index into d_act
+    auto hw = [&](Group& g, int din, int dout) {
+        g.a.Hin = H / din; g.a.Win = W / din; g.a.Hout = H / dout; g.a.Wout = W / dout;
+    };
+    const float* prev = nullptr;
+    auto chain = [&](Group g, int din, int dout) {
+        hw(g, din, dout);
+        g.a.x = prev;
+        g.a.y = ctx->d_act[ai++];
+        prev = g.a.y;
+        G.push_back(g);
+    };
+    {
+        Group g{}; g.name = "conv1_4"; g.launch = &launch_stem; g.out_ch = 4;
+        g.a.Hin = H; g.a.Win = W; g.a.Hout = H / 2; g.a.Wout = W / 2;
+        g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
+    }
+    chain(make_irb<CfgRes1>("res1_1", 4), 2, 2);
+    { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense; g.out_ch = 8; chain(g, 2, 4); }
+    chain(make_irb<CfgRes2>("res2_1", 8), 4, 4);
+    chain(make_irb<CfgRes2>("res2_2", 8), 4, 4);
+    chain(make_irb<CfgDown2>("conv3_1", 8), 4, 8);
+    chain(make_irb<CfgRes3a>("res3_1", 8), 8, 8);
+    chain(make_irb<CfgRes3a>("res3_2", 8), 8, 8);
+    chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
+    chain(make_irb<CfgRes3b>("res3_3", 16), 8, 8);
+    chain(make_irb<CfgRes3b>("res3_4", 16), 8, 8);
+    chain(make_irb<CfgRes3b>("res3_5", 16), 8, 8);
+    chain(make_irb<CfgRes3b>("res3_6", 16), 8, 8);
+    chain(make_irb<CfgDown3>("conv4_1", 24), 8, 16);
+    chain(make_irb<CfgRes4>("res4_1", 24), 16, 16);
+    chain(make_irb<CfgRes4>("res4_2", 24), 16, 16);
+    chain(make_irb<CfgRes4>("res4_3", 24), 16, 16);
+    chain(make_irb<CfgRes4>("res4_4", 24), 16, 16);
+    {
+        Group g = make_irb<CfgDown4>("conv5_1", 48);
+        g.a.skip = ctx->d_skip;
+        chain(g, 16, 32);
+    }
+    chain(make_irb<CfgRes5>("res5_1", 48), 32, 32);
+    chain(make_irb<CfgRes5>("res5_2", 48), 32, 32);
+    chain(make_irb<CfgRes5>("res5_3", 48), 32, 32);
+    chain(make_irb<CfgRes5>("res5_4", 48), 32, 32);
+    chain(make_irb<CfgRes5>("res5_5", 48), 32, 32);
+    { Group g{}; g.name = "conv5_2"; g.launch = &launch_pw52; g.out_ch = 96; chain(g, 32, 32); }
+    const float* conv5_2 = prev;
+    chain(make_irb<CfgNeckS1>("conv5_4", 128), 32, 32);
+    {
+        Group g = make_irb<CfgNeckS2>("head_5", 0);   // y = caller's head_small, set per call
+        hw(g, 32, 32); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
+    }
+    {
+        Group g{}; g.name = "conv4_1_1"; g.launch = &launch_upcat; g.out_ch = 96;
+        hw(g, 16, 16); g.a.x = ctx->d_skip; g.a.x2 = conv5_2; g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
+    }
+    chain(make_irb<CfgNeckL1>("conv4_1_3", 96), 16, 16);
+    {
+        Group g = make_irb<CfgNeckL2>("head_4", 0);   // y = caller's head_large
+        hw(g, 16, 16); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
+    }
+}
+
+extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors, int max_batch, int H, int W) {
+    if (!out) { set_err(nullptr, "out is null"); return YF_ERR_ARG; }
+    *out = nullptr;
+    if (in_ch != 1) { set_err(nullptr, "in_ch=%d unsupported: the shipped models are single-channel (_config.py:10)", in_ch); return YF_ERR_ARG; }
+    if (num_cls < 1 || num_cls > POST_MAX_CLS || num_anchors < 1 || num_anchors > YF_MAX_ANCHORS || max_batch < 1) {
+        set_err(nullptr, "bad num_cls/num_anchors/max_batch (%d, %d, %d)", num_cls, num_anchors, max_batch);
+        return YF_ERR_ARG;
+    }
+    if (H < 32 || W < 32 || H % 32 || W % 32) { set_err(nullptr, "H, W must be positive multiples of 32 (got %dx%d)", H, W); return YF_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        set_err(nullptr, "no usable CUDA device %d (%s); this library has no CPU fallback", device,
+                e != cudaSuccess ? cudaGetErrorString(e) : "index out of range");
+        return YF_ERR_CUDA;
+    }
+    yf_ctx* ctx = new yf_ctx();
+    ctx->device = device; ctx->in_ch = in_ch; ctx->num_cls = num_cls; ctx->num_anchors = num_anchors;
+    ctx->max_batch = max_batch; ctx->H = H; ctx->W = W;
+    ctx->nout = num_anchors * (5 + num_cls);
+    ctx->specs = build_specs(in_ch, num_cls, num_anchors);
+    auto fail = [&](int rc) { g_err = ctx->err; yf_destroy(ctx); return rc; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { set_err(&ctx->err, "cudaSetDevice: %s", cudaGetErrorString(e)); return fail(YF_ERR_CUDA); }
+    cudaError_t ie[] = {
+        cudaFuncSetAttribute(stem_kernel<CfgStem, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem::SMEM_BYTES),
+        cudaFuncSetAttribute(stem_kernel<CfgStem, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem::SMEM_BYTES),
+        cudaFuncSetAttribute(dense_kernel<CfgDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDense::SMEM_BYTES),
+        cudaFuncSetAttribute(pw_kernel<CfgPw52>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPw52::SMEM_BYTES),
+        cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
+        init_irb<CfgRes1>(), init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
+        init_irb<CfgRes3b>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
+    for (cudaError_t x : ie)
+        if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
+    int rc = alloc_all(ctx);
+    if (rc != YF_OK) return fail(rc);
+    build_plan(ctx);
+    *out = ctx;
+    return YF_OK;
+}
+
+extern "C" void yf_destroy(yf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (float* p : ctx->d_act) cudaFree(p);
+    cudaFree(ctx->d_w); cudaFree(ctx->d_skip); cudaFree(ctx->d_hl); cudaFree(ctx->d_hs); cudaFree(ctx->d_x); cudaFree(ctx->d_u8);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
+    cudaFree(ctx->p_rec); cudaFree(ctx->p_conf); cudaFree(ctx->p_cls); cudaFree(ctx->p_sbox); cudaFree(ctx->p_order);
+    cudaFree(ctx->p_alive); cudaFree(ctx->n_alive);
+    delete ctx;
+}
+
+extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_floats) {
+    CTX_CHECK(ctx);
+    if (!host_blob || n_floats != ctx->specs.total) {
+        set_err(&ctx->err, "weight blob has %lld floats, expected %lld", (long long)n_floats, (long long)ctx->specs.total);
+        return YF_ERR_ARG;
+    }
+    for (int64_t i = 0; i < n_floats; ++i)
+        if (!std::isfinite(host_blob[i])) { set_err(&ctx->err, "non-finite weight at %lld", (long long)i); return YF_ERR_ARG; }
+    CU(cudaSetDevice(ctx->device));
+    Folded f{host_blob, &ctx->specs};
+    std::vector<float>& P = ctx->host_packed;
+    P.clear();
+    std::vector<int64_t> offs;
+    auto res = [&](auto tag, const std::string& n) {
+        using C = decltype(tag);
+        offs.push_back(pack_irb<C>(P, f, n + ".conv1", n + ".conv2", n + ".conv3", "", 0));
+    };
+    offs.push_back(pack_stem(P, f));
+    res(CfgRes1{}, "res1_1");
+    offs.push_back(pack_dense(P, f));
+    res(CfgRes2{}, "res2_1"); res(CfgRes2{}, "res2_2");
+    offs.push_back(pack_irb<CfgDown2>(P, f, "conv2_2", "conv2_3", "conv3_1", "", 0));
+    res(CfgRes3a{}, "res3_1"); res(CfgRes3a{}, "res3_2");
+    offs.push_back(pack_irb<CfgWide3>(P, f, "conv3_2", "conv3_3", "conv3_4", "", 0));
+    res(CfgRes3b{}, "res3_3"); res(CfgRes3b{}, "res3_4"); res(CfgRes3b{}, "res3_5"); res(CfgRes3b{}, "res3_6");
+    offs.push_back(pack_irb<CfgDown3>(P, f, "conv3_5", "conv3_6", "conv4_1", "", 0));
+    res(CfgRes4{}, "res4_1"); res(CfgRes4{}, "res4_2"); res(CfgRes4{}, "res4_3"); res(CfgRes4{}, "res4_4");
+    offs.push_back(pack_irb<CfgDown4>(P, f, "conv4_2", "conv4_3", "conv5_1", "", 0));
+    res(CfgRes5{}, "res5_1"); res(CfgRes5{}, "res5_2"); res(CfgRes5{}, "res5_3"); res(CfgRes5{}, "res5_4"); res(CfgRes5{}, "res5_5");
+    offs.push_back(pack_pw52(P, f));
+    offs.push_back(pack_irb<CfgNeckS1>(P, f, "", "conv5_3", "conv5_4", "", 0));
+    offs.push_back(pack_irb<CfgNeckS2>(P, f, "", "conv5_5", "conv5_6", "head_5", ctx->nout));
+    offs.push_back(pack_upcat(P, f));
+    offs.push_back(pack_irb<CfgNeckL1>(P, f, "", "conv4_1_2", "conv4_1_3", "", 0));
+    offs.push_back(pack_irb<CfgNeckL2>(P, f, "", "conv4_1_4", "conv4_1_5", "head_4", ctx->nout));
+    pad4(P);
+    if (offs.size() != ctx->groups.size()) { set_err(&ctx->err, "internal: %zu packs vs %zu groups", offs.size(), ctx->groups.size()); return YF_ERR_STATE; }
+    if (ctx->d_w) CU(cudaFree(ctx->d_w));
+    ctx->d_w = nullptr;
+    CU(cudaMalloc(&ctx->d_w, sizeof(float) * P.size()));
+    CU(cudaMemcpy(ctx->d_w, P.data(), sizeof(float) * P.size(), cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < offs.size(); ++i) { ctx->groups[i].w_off = offs[i]; ctx->groups[i].a.w = ctx->d_w + offs[i]; }
+    ctx->weights_loaded = true;
+    return YF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* head_large, float* head_small, cudaStream_t st) {
+    if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
+    if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
+    if (!x || !head_large || !head_small) { set_err(&ctx->err, "null tensor pointer"); return YF_ERR_ARG; }
+    for (Group& g : ctx->groups) {
+        GroupArgs a = g.a;
+        if (!strcmp(g.name, "head_5")) a.y = head_small;
+        if (!strcmp(g.name, "head_4")) a.y = head_large;
+        g.launch(a, x, u8in, B, st);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return YF_OK;
+}
+
+extern "C" int yf_forward(yf_ctx* ctx, const float* x, int B, float* head_large, float* head_small, void* stream) {
+    CTX_CHECK(ctx);
+    return forward_impl(ctx, x, false, B, head_large, head_small, (cudaStream_t)stream);
+}
+
+extern "C" int yf_tap(yf_ctx* ctx, const char* name, int B, float* dst, int64_t* per_image, void* stream) {
+    CTX_CHECK(ctx);
+    auto it = ctx->taps.find(name ? name : "");
+    if (it == ctx->taps.end()) { set_err(&ctx->err, "no tap named '%s'", name ? name : "(null)"); return YF_ERR_ARG; }
+    if (per_image) *per_image = it->second.second;
+    if (dst) {
+        if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "bad batch %d", B); return YF_ERR_STATE; }
+        CU(cudaMemcpyAsync(dst, it->second.first, sizeof(float) * it->second.second * B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return YF_OK;
+}
+
+extern "C" int yf_profile_forward(yf_ctx* ctx, const float* x, int B, const char** names, float* ms, int cap) {
+    CTX_CHECK(ctx);
+    if (!ctx->weights_loaded) { set_err(&ctx->err, "weights not loaded"); return YF_ERR_STATE; }
+    if (B < 1 || B > ctx->max_batch || !x) { set_err(&ctx->err, "bad arguments"); return YF_ERR_ARG; }
+    const int n = (int)ctx->groups.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    for (int rep = 0; rep < 2; ++rep) {   // first pass warms up, second is reported
+        CU(cudaEventRecord(ev[0], 0));
+        for (int i = 0; i < n; ++i) {
+            Group& g = ctx->groups[i];
+            GroupArgs a = g.a;
+            if (!strcmp(g.name, "head_5")) a.y = ctx->d_hs;
+            if (!strcmp(g.name, "head_4")) a.y = ctx->d_hl;
+            g.launch(a, x, false, B, 0);
+            ctx->launches++;
+            CU(cudaEventRecord(ev[i + 1], 0));
+        }
+        CU(cudaDeviceSynchronize());
+    }
+    int w = 0;
+    for (int i = 0; i < n && w < cap; ++i, ++w) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+        if (names) names[w] = ctx->groups[i].name;
+        if (ms) ms[w] = t;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// post-processing
+// ---------------------------------------------------------------------------------------------
+static int post_impl(yf_ctx* ctx, const float* hl, const float* hs, int B, int hlh, int hlw, int hsh, int hsw,
+                     const yf_post_params* p, yf_det* out, int32_t* counts, int32_t* status, int do_nms, cudaStream_t st) {
+    if (!p || !hl || !hs || !out || !counts) { set_err(&ctx->err, "null argument"); return YF_ERR_ARG; }
+    if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
+    if (p->mode != YF_MODE_DETECT && p->mode != YF_MODE_VALIDATE) { set_err(&ctx->err, "bad mode %d", p->mode); return YF_ERR_ARG; }
+    if (p->max_det < 1) { set_err(&ctx->err, "max_det must be >= 1"); return YF_ERR_ARG; }
+    const int NC = ctx->num_anchors * (hlh * hlw + hsh * hsw);
+    if (NC > ctx->NC || NC < 1) { set_err(&ctx->err, "%d candidates exceed the ctx capacity %d (created for %dx%d)", NC, ctx->NC, ctx->H, ctx->W); return YF_ERR_STATE; }
+    PostArgs a;
+    memset(&a, 0, sizeof a);
+    a.head[0] = hl; a.head[1] = hs;
+    a.A = ctx->num_anchors; a.nc = ctx->num_cls;
+    a.h[0] = hlh; a.w[0] = hlw; a.h[1] = hsh; a.w[1] = hsw;
+    memcpy(a.anchors, p->anchors, sizeof a.anchors);
+    a.conf_thres = p->conf_thres; a.nms_thres = p->nms_thres;
+    a.input_h = p->input_h; a.input_w = p->input_w; a.mode = p->mode; a.max_det = p->max_det; a.do_nms = do_nms;
+    a.out = out; a.counts = counts; a.status = status;
+    a.NC = NC;
+    a.rec = ctx->p_rec; a.conf = ctx->p_conf; a.cls = ctx->p_cls; a.sbox = ctx->p_sbox; a.order = ctx->p_order; a.alive = ctx->p_alive;
+    if (p->mode == YF_MODE_DETECT) post_kernel<YF_MODE_DETECT><<<B, POST_NT, 0, st>>>(a);
+    else post_kernel<YF_MODE_VALIDATE><<<B, POST_NT, 0, st>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return YF_OK;
+}
+
+extern "C" int yf_postprocess(yf_ctx* ctx, const float* head_large, const float* head_small, int B, int hl, int wl, int hs, int ws,
+                              const yf_post_params* p, yf_det* out, int32_t* counts, int32_t* status, void* stream) {
+    CTX_CHECK(ctx);
+    return post_impl(ctx, head_large, head_small, B, hl, wl, hs, ws, p, out, counts, status, 1, (cudaStream_t)stream);
+}
+
+extern "C" int yf_decode(yf_ctx* ctx, const float* head_large, const float* head_small, int B, int hl, int wl, int hs, int ws,
+                         const yf_post_params* p, yf_det* out, int32_t* counts, int32_t* status, void* stream) {
+    CTX_CHECK(ctx);
+    return post_impl(ctx, head_large, head_small, B, hl, wl, hs, ws, p, out, counts, status, 0, (cudaStream_t)stream);
+}
+
+extern "C" int yf_val_decode(yf_ctx* ctx, const float* head, int B, int h, int w, const double* anchors, int num_anchors,
+                             int num_cls, int input_h, int input_w, float* out, void* stream) {
+    CTX_CHECK(ctx);
+    if (!head || !anchors || !out || B < 1 || h < 1 || w < 1 || num_anchors < 1 || num_anchors > YF_MAX_ANCHORS || num_cls < 1) {
+        set_err(&ctx->err, "bad argument"); return YF_ERR_ARG;
+    }
+    ValDecodeArgs a;
+    a.head = head; a.out = out; a.B = B; a.A = num_anchors; a.nc = num_cls; a.h = h; a.w = w;
+    const double sw = (double)input_w / (double)w, sh = (double)input_h / (double)h;
+    a.stride_w = (float)sw; a.stride_h = (float)sh;
+    for (int i = 0; i < num_anchors; ++i) { a.aw[i] = (float)(anchors[2 * i] / sw); a.ah[i] = (float)(anchors[2 * i + 1] / sh); }
+    const long long total = (long long)B * num_anchors * h * w;
+    val_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return YF_OK;
+}
+
+extern "C" int yf_val_nms(yf_ctx* ctx, const float* pred, int B, int N, double conf_thres, double nms_thres, int max_det,
+                          yf_det* out, int32_t* counts, int32_t* status, void* stream) {
+    CTX_CHECK(ctx);
+    if (!pred || !out || !counts || max_det < 1) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
+    if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
+    if (N < 1 || N > ctx->NC) { set_err(&ctx->err, "%d rows exceed the ctx capacity %d", N, ctx->NC); return YF_ERR_STATE; }
+    PostArgs a;
+    memset(&a, 0, sizeof a);
+    a.pred = pred;
+    a.A = ctx->num_anchors; a.nc = ctx->num_cls;
+    a.conf_thres = conf_thres; a.nms_thres = nms_thres;
+    a.mode = YF_MODE_VALIDATE; a.max_det = max_det; a.do_nms = 1;
+    a.out = out; a.counts = counts; a.status = status;
+    a.NC = N;
+    a.rec = ctx->p_rec; a.conf = ctx->p_conf; a.cls = ctx->p_cls; a.sbox = ctx->p_sbox; a.order = ctx->p_order; a.alive = ctx->p_alive;
+    post_kernel<POST_SRC_ROWS><<<B, POST_NT, 0, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return YF_OK;
+}
+
+static int nms_scratch(yf_ctx* ctx, int n) {
+    if (n <= ctx->n_alive_cap) return YF_OK;
+    if (ctx->n_alive) CU(cudaFree(ctx->n_alive));
+    ctx->n_alive = nullptr;
+    CU(cudaMalloc(&ctx->n_alive, (size_t)n));
+    ctx->n_alive_cap = n;
+    return YF_OK;
+}
+
+extern "C" int yf_nms_sorted_i32(yf_ctx* ctx, const int32_t* boxes, int n, double nms_thres, int32_t* keep, int32_t* n_keep, void* stream) {
+    CTX_CHECK(ctx);
+    if (!boxes || !keep || !n_keep || n < 0) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
+    int rc = nms_scratch(ctx, n > 0 ? n : 1);
+    if (rc) return rc;
+    nms_sorted_kernel<YF_MODE_DETECT><<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int4*>(boxes), ctx->n_alive, n, nms_thres, 0.f, keep, n_keep);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return YF_OK;
+}
+
+extern "C" int yf_nms_sorted_f32(yf_ctx* ctx, const float* boxes_f, int n, float nms_thres, int32_t* keep, int32_t* n_keep, void* stream) {
+    CTX_CHECK(ctx);
+    if (!boxes_f || !keep || !n_keep || n < 0) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
+    int rc = nms_scratch(ctx, n > 0 ? n : 1);
+    if (rc) return rc;
+    nms_sorted_kernel<YF_MODE_VALIDATE><<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int4*>(boxes_f), ctx->n_alive, n, 0.0, nms_thres, keep, n_keep);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return YF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused paths
+// ---------------------------------------------------------------------------------------------
+static int detect_impl(yf_ctx* ctx, const void* x, bool u8in, int B, const yf_post_params* p, yf_det* out, int32_t* counts,
+                       int32_t* status, cudaStream_t st) {
+    int rc = forward_impl(ctx, x, u8in, B, ctx->d_hl, ctx->d_hs, st);
+    if (rc) return rc;
+    return post_impl(ctx, ctx->d_hl, ctx->d_hs, B, ctx->H / 16, ctx->W / 16, ctx->H / 32, ctx->W / 32, p, out, counts, status, 1, st);
+}
+
+extern "C" int yf_detect(yf_ctx* ctx, const float* x, int B, const yf_post_params* p, yf_det* out, int32_t* counts,
+                         int32_t* status, void* stream) {
+    CTX_CHECK(ctx);
+    return detect_impl(ctx, x, false, B, p, out, counts, status, (cudaStream_t)stream);
+}
+
+static int detect_host_impl(yf_ctx* ctx, const void* x_host, bool u8in, int B, const yf_post_params* p, yf_det* out_host,
+                            int32_t* counts_host, int32_t* status_host, cudaStream_t st) {
+    if (!x_host || !p || !out_host || !counts_host) { set_err(&ctx->err, "null argument"); return YF_ERR_ARG; }
+    if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
+    if (p->max_det < 1) { set_err(&ctx->err, "max_det must be >= 1"); return YF_ERR_ARG; }
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_out(ctx, p->max_det);
+    if (rc) return rc;
+    const size_t npx = (size_t)B * ctx->in_ch * ctx->H * ctx->W;
+    const void* xdev;
+    if (u8in) { CU(cudaMemcpyAsync(ctx->d_u8, x_host, npx, cudaMemcpyHostToDevice, st)); xdev = ctx->d_u8; }
+    else { CU(cudaMemcpyAsync(ctx->d_x, x_host, npx * sizeof(float), cudaMemcpyHostToDevice, st)); xdev = ctx->d_x; }
+    rc = detect_impl(ctx, xdev, u8in, B, p, ctx->d_out, ctx->d_counts, ctx->d_status, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_host, ctx->d_out, sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(counts_host, ctx->d_counts, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    if (status_host) CU(cudaMemcpyAsync(status_host, ctx->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return YF_OK;
+}
+
+extern "C" int yf_detect_host(yf_ctx* ctx, const float* x_host, int B, const yf_post_params* p, yf_det* out_host,
+                              int32_t* counts_host, int32_t* status_host, void* stream) {
+    CTX_CHECK(ctx);
+    return detect_host_impl(ctx, x_host, false, B, p, out_host, counts_host, status_host, (cudaStream_t)stream);
+}
+
+extern "C" int yf_detect_host_u8(yf_ctx* ctx, const uint8_t* u8_host, int B, const yf_post_params* p, yf_det* out_host,
+                                 int32_t* counts_host, int32_t* status_host, void* stream) {
+    CTX_CHECK(ctx);
+    return detect_host_impl(ctx, u8_host, true, B, p, out_host, counts_host, status_host, (cudaStream_t)stream);
+}
+
+extern "C" int64_t yf_launch_count(const yf_ctx* ctx) { return ctx ? ctx->launches : -1; }

@@ -1,0 +1,903 @@
+// yf_kernels.cuh — fused forward kernels of the YOLO-Fastest hot path for sm_100a.
+//
+// Data layout: activations are planar fp32 [B][C][H][W] in HBM — the reference's own NCHW
+// (yolo_fastest.py:150-218).  A CTA owns one spatial tile of one image; every stage keeps its
+// operands in shared memory as [channel][tile pixel], so the 32 lanes of a warp walk consecutive
+// pixels (conflict-free 128-bit LDS, coalesced 128-bit STG) while weights are warp-broadcast.
+// Each fused group keeps its intermediate activations on chip:
+//
+//   pw_halo   1x1 conv + bias + ReLU over the halo tile         (conv_norm_relu k=1, yolo_fastest.py:16-26)
+//   dw_stage  depthwise KxK stride S + bias + ReLU, sliding window in registers   (groups=C, :57,81,95,...)
+//   pw_accum  1x1 conv accumulated over mid-channel chunks into per-thread register tiles (:58,82,...)
+//
+// The mid channels of an inverted-residual block are processed in chunks of MC so shared memory
+// holds only [MC][halo] + [MC][tile] floats whatever the expansion width (8..224).
+// BatchNorm is folded into the weights on the host (eval-mode BN is affine).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace yf {
+
+constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+constexpr int rup(int a, int b) { return cdiv(a, b) * b; }
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// Tile geometry of a KSxKS stride-S stage producing a TH x TW output tile.
+template <int KS_, int S_, int TH_, int TW_>
+struct Geo {
+    static constexpr int KS = KS_, S = S_, TH = TH_, TW = TW_;
+    static constexpr int P = (KS - 1) / 2;            // zero padding (k-1)//2, yolo_fastest.py:17-19
+    static constexpr int IH = (TH - 1) * S + KS;      // halo tile rows
+    static constexpr int IW = (TW - 1) * S + KS;      // halo tile columns actually needed
+    static constexpr int IWS = rup(IW, 4);            // row stride in smem (float4 aligned)
+    static constexpr int IPIX = IH * IWS;
+    static constexpr int OPIX = TH * TW;
+    static_assert(TW % 4 == 0, "tile width must be a multiple of 4");
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Cooperative copy of n floats (n % 4 == 0, both 16B aligned) global -> shared.
+template <int NT>
+__device__ __forceinline__ void copy_f4(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    for (int i = threadIdx.x * 4; i < n; i += NT * 4) st4(dst + i, __ldg(reinterpret_cast<const float4*>(src + i)));
+}
+
+// Load an [nch][RH][RW] rectangle (zero outside the image, zero in the pad columns >= RW) of a
+// planar image into smem [nch][RH][RWS]. src points at channel 0 of the image.
+template <int RH, int RW, int RWS, int NT>
+__device__ __forceinline__ void load_rect(float* __restrict__ dst, const float* __restrict__ src, int nch, int nch_valid,
+                                          int Hin, int Win, int iy0, int ix0) {
+    constexpr int RPIX = RH * RWS;
+    for (int idx = threadIdx.x; idx < nch * RPIX; idx += NT) {
+        const int c = idx / RPIX;
+        const int rem = idx - c * RPIX;
+        const int r = rem / RWS;
+        const int j = rem - r * RWS;
+        const int gy = iy0 + r, gx = ix0 + j;
+        float v = 0.f;
+        if (c < nch_valid && j < RW && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win)
+            v = __ldg(src + ((size_t)c * Hin + gy) * Win + gx);
+        dst[idx] = v;
+    }
+}
+
+// Stage 1: E[m][p] = mask(p) * relu(sum_k W[k][m] X[k][p] + b[m]) over the whole halo tile.
+// mask(p) = pixel p lies inside the image: the depthwise conv that follows zero-pads ITS input,
+// i.e. the activation, not the bias (yolo_fastest.py:17-22).
+// Thread item = 4 consecutive halo pixels x PN mid channels.  W is [K][MC] in smem.
+// DUAL additionally writes the tile-owned pixels to `skip` (global, [MC..][Hin][Win] of this image).
+template <class G, int K, int MC, int PN, int NT, bool DUAL>
+__device__ __forceinline__ void pw_halo(const float* __restrict__ Xs, const float* __restrict__ W,
+                                        const float* __restrict__ bias, float* __restrict__ Es,
+                                        int iy0, int ix0, int Hin, int Win,
+                                        float* __restrict__ skip, int skip_valid) {
+    static_assert(PN % 4 == 0 && MC % PN == 0, "bad PN");
+    constexpr int NPG = G::IPIX / 4;
+    constexpr int NCG = MC / PN;
+    for (int item = threadIdx.x; item < NPG * NCG; item += NT) {
+        const int cg = item / NPG;
+        const int pg = item - cg * NPG;
+        const int p0 = pg * 4;
+        const int r = p0 / G::IWS;
+        const int j0 = p0 - r * G::IWS;
+        const int gy = iy0 + r, gx0 = ix0 + j0;
+        float* e = Es + cg * PN * G::IPIX + p0;
+        const bool rowok = (unsigned)gy < (unsigned)Hin;
+        bool m[4];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            m[i] = rowok && (j0 + i < G::IW) && ((unsigned)(gx0 + i) < (unsigned)Win);
+            any |= m[i];
+        }
+        if (!any) {
+#pragma unroll
+            for (int n = 0; n < PN; ++n) st4(e + n * G::IPIX, make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
+        float acc[PN][4];
+#pragma unroll
+        for (int n4 = 0; n4 < PN / 4; ++n4) {
+            const float4 b = ld4(bias + cg * PN + n4 * 4);
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[n4 * 4 + q][i] = bb[q];
+        }
+        const float* xp = Xs + p0;
+        const float* wp = W + cg * PN;
+#pragma unroll 8
+        for (int k = 0; k < K; ++k) {
+            const float4 xv = ld4(xp + k * G::IPIX);
+            const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int n4 = 0; n4 < PN / 4; ++n4) {
+                const float4 w = ld4(wp + k * MC + n4 * 4);
+                const float w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[n4 * 4 + q][i] = fmaf(w4[q], x4[i], acc[n4 * 4 + q][i]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < PN; ++n) {
+            float4 o;
+            o.x = m[0] ? fmaxf(acc[n][0], 0.f) : 0.f;
+            o.y = m[1] ? fmaxf(acc[n][1], 0.f) : 0.f;
+            o.z = m[2] ? fmaxf(acc[n][2], 0.f) : 0.f;
+            o.w = m[3] ? fmaxf(acc[n][3], 0.f) : 0.f;
+            st4(e + n * G::IPIX, o);
+            if (DUAL) {
+                // pixels this tile owns (not halo): rows/cols [P, P + T*S)
+                const bool rown = r >= G::P && r < G::P + G::TH * G::S;
+                if (rown && (cg * PN + n) < skip_valid) {
+                    float* sp = skip + ((size_t)(cg * PN + n) * Hin + gy) * Win + gx0;
+                    const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = j0 + i;
+                        if (m[i] && j >= G::P && j < G::P + G::TW * G::S) sp[i] = ov[i];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void load_row(float (&dst)[NV], const float* __restrict__ p) {
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+        const float4 v = ld4(p + 4 * i);
+        dst[4 * i + 0] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+    }
+    if (NV % 4 >= 2) {
+        const float2 v = *reinterpret_cast<const float2*>(p + (NV / 4) * 4);
+        dst[(NV / 4) * 4 + 0] = v.x; dst[(NV / 4) * 4 + 1] = v.y;
+    }
+    if (NV % 2 == 1) dst[NV - 1] = p[NV - 1];
+}
+
+// Stage 2: depthwise KSxKS stride S + bias + ReLU:  D[m][oy][ox] = relu(sum W[m][dy][dx] E[m][oy*S+dy][ox*S+dx] + b[m]).
+// Thread item = one channel x a strip of 4 output columns x RH output rows; the KS input rows of
+// the window live in registers and slide down (S new row loads per output row).
+template <class G, int MC, int RH, int NT>
+__device__ __forceinline__ void dw_stage(const float* __restrict__ Es, const float* __restrict__ Wd,
+                                         const float* __restrict__ bd, float* __restrict__ Ds) {
+    constexpr int KS = G::KS, S = G::S;
+    static_assert(G::TH % RH == 0, "RH must divide TH");
+    static_assert(KS > S, "window must overlap");
+    constexpr int NSTRIP = G::TW / 4, NSEG = G::TH / RH;
+    constexpr int NV = 3 * S + KS;   // input columns feeding 4 adjacent outputs
+    constexpr int NITEM = MC * NSEG * NSTRIP;
+    for (int item = threadIdx.x; item < NITEM; item += NT) {
+        const int m = item / (NSEG * NSTRIP);
+        const int rem = item - m * (NSEG * NSTRIP);
+        const int seg = rem / NSTRIP;
+        const int g = rem - seg * NSTRIP;
+        float w[KS * KS];
+#pragma unroll
+        for (int t = 0; t < KS * KS; ++t) w[t] = Wd[m * KS * KS + t];
+        const float b = bd[m];
+        const float* e = Es + m * G::IPIX + (seg * RH * S) * G::IWS + 4 * g * S;
+        float* d = Ds + m * G::OPIX + (seg * RH) * G::TW + 4 * g;
+        float win[KS][NV];
+#pragma unroll
+        for (int dd = 0; dd < KS - S; ++dd) load_row<NV>(win[dd + S], e + dd * G::IWS);
+#pragma unroll
+        for (int oy = 0; oy < RH; ++oy) {
+#pragma unroll
+            for (int dd = 0; dd < KS - S; ++dd)
+#pragma unroll
+                for (int v = 0; v < NV; ++v) win[dd][v] = win[dd + S][v];
+#pragma unroll
+            for (int dd = KS - S; dd < KS; ++dd) load_row<NV>(win[dd], e + (oy * S + dd) * G::IWS);
+            float a[4] = {b, b, b, b};
+#pragma unroll
+            for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = fmaf(w[dy * KS + dx], win[dy][i * S + dx], a[i]);
+            st4(d + oy * G::TW, make_float4(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f), fmaxf(a[2], 0.f), fmaxf(a[3], 0.f)));
+        }
+    }
+}
+
+// Stage 3: acc[n][p] += sum_{m < KC} W[m][n] D[m][p]; thread item = 4 consecutive pixels x PN out
+// channels, IPT items per thread, accumulators persist in registers across chunks.
+template <int OPIX, int KC, int N, int PN, int IPT, int NT>
+__device__ __forceinline__ void pw_accum(const float* __restrict__ Ds, const float* __restrict__ W,
+                                         float (&acc)[IPT][PN][4]) {
+    static_assert(PN % 4 == 0 && N % PN == 0 && OPIX % 4 == 0, "bad pw_accum tiling");
+    constexpr int NPG = OPIX / 4;
+    constexpr int NCG = N / PN;
+#pragma unroll
+    for (int it = 0; it < IPT; ++it) {
+        const int item = threadIdx.x + it * NT;
+        if (item < NPG * NCG) {
+            const int cg = item / NPG;
+            const int pg = item - cg * NPG;
+            const float* dp = Ds + pg * 4;
+            const float* wp = W + cg * PN;
+#pragma unroll 8
+            for (int m = 0; m < KC; ++m) {
+                const float4 dv = ld4(dp + m * OPIX);
+                const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                for (int n4 = 0; n4 < PN / 4; ++n4) {
+                    const float4 w = ld4(wp + m * N + n4 * 4);
+                    const float w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[it][n4 * 4 + q][i] = fmaf(w4[q], d4[i], acc[it][n4 * 4 + q][i]);
+                }
+            }
+        }
+    }
+}
+
+// Store 4 consecutive pixels of one output channel row (guarded; 128-bit when aligned).
+__device__ __forceinline__ void store_px4(float* __restrict__ rowp, int gx0, int Wout, const float (&v)[4]) {
+    if (((Wout & 3) == 0) && gx0 + 3 < Wout) {
+        st4(rowp + gx0, make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (gx0 + i < Wout) rowp[gx0 + i] = v[i];
+    }
+}
+
+struct TileId { int b, ty, tx; };
+__device__ __forceinline__ TileId tile_id(int tiles_x, int tiles_y) {
+    int t = blockIdx.x;
+    TileId id;
+    id.tx = t % tiles_x; t /= tiles_x;
+    id.ty = t % tiles_y;
+    id.b = t / tiles_y;
+    return id;
+}
+
+// ---------------------------------------------------------------------------------------------
+// IRB engine: [1x1 expand + ReLU] -> depthwise KxK (stride S) + ReLU -> 1x1 project (+bias)
+//             (+ residual) (+ ReLU) [-> 1x1 head with bias]
+// Covers BasicResBlock (yolo_fastest.py:52-66), the strided transition triples (:94-97,111-114),
+// conv4_2/conv4_3/conv5_1 with the conv4_2 skip output (:121-124,190), and with EXPAND=false the
+// neck pairs dw5x5 -> 1x1 (:133-136,143-146) including the biased head convs (:138,148).
+// Packed weights (floats): NCHUNK x { [W1: CIN*MC][b1: MC] (EXPAND only) [Wd: MC*KS*KS][bd: MC][W2: MC*COUT] },
+// then [b2: COUT], then (HEADN > 0: group ends in a head conv) [Wh: COUT*headp][bh: headp] with headp = rup(headn, 4),
+// headn = num_anchors * (5 + num_cls) given at run time.
+// ---------------------------------------------------------------------------------------------
+template <int CIN_, int CMID_, int COUT_, int KS_, int S_, int TH_, int TW_, int MC_, int PN1_, int PN3_, int RH_,
+          int NT_, int MINB_, bool EXPAND_, bool RES_, bool RELU_OUT_, bool DUAL_, int HEADN_ = 0>
+struct IrbCfg {
+    static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_, MC = MC_, PN1 = PN1_, PN3 = PN3_, RH = RH_;
+    static constexpr int NT = NT_, MINB = MINB_, HEADN = HEADN_;
+    static constexpr bool EXPAND = EXPAND_, RES = RES_, RELU_OUT = RELU_OUT_, DUAL = DUAL_;
+    using G = Geo<KS_, S_, TH_, TW_>;
+    static constexpr int KK = KS_ * KS_;
+    static constexpr int CMIDP = rup(CMID, MC);
+    static constexpr int NCHUNK = CMIDP / MC;
+    static constexpr int OFF_W1 = 0;
+    static constexpr int OFF_B1 = OFF_W1 + (EXPAND ? CIN * MC : 0);
+    static constexpr int OFF_WD = OFF_B1 + (EXPAND ? MC : 0);
+    static constexpr int OFF_BD = OFF_WD + MC * KK;
+    static constexpr int OFF_W2 = OFF_BD + MC;
+    static constexpr int CB = OFF_W2 + MC * COUT;              // floats per chunk block
+    static constexpr int OFF_B2 = NCHUNK * CB;
+    static constexpr int OFF_WH = OFF_B2 + COUT;             // head weights [COUT][headp], then bias [headp] (runtime headn)
+    static constexpr int XS = EXPAND ? CIN * G::IPIX : 0;
+    static constexpr int ES = MC * G::IPIX;
+    static constexpr int DS = MC * G::OPIX;
+    static constexpr int ACT = cmax(XS + ES + DS, HEADN > 0 ? COUT * G::OPIX : 0);
+    static constexpr int SMEM_FLOATS = ACT + 2 * CB;
+    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+    static constexpr int NPG3 = G::OPIX / 4, NCG3 = COUT / PN3;
+    static constexpr int IPT = cdiv(NPG3 * NCG3, NT);
+    static_assert(MC % 4 == 0 && COUT % 4 == 0 && CB % 4 == 0, "alignment");
+    static_assert(!RES || (CIN == COUT && S_ == 1 && EXPAND), "residual needs same shape");
+    static_assert(EXPAND || CMID == CIN, "dw-first groups have CMID == CIN");
+    static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB)
+irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ skip, const float* __restrict__ wts,
+           int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y, int headn) {
+    using G = typename C::G;
+    constexpr int NT = C::NT;
+    extern __shared__ __align__(16) float smem[];
+    float* Xs = smem;
+    float* Es = Xs + C::XS;
+    float* Ds = Es + C::ES;
+    float* Ws = smem + C::ACT;
+
+    const TileId t = tile_id(tiles_x, tiles_y);
+    const int oy0 = t.ty * G::TH, ox0 = t.tx * G::TW;
+    const int iy0 = oy0 * G::S - G::P, ix0 = ox0 * G::S - G::P;
+    const float* xb = x + (size_t)t.b * C::CIN * Hin * Win;
+
+    if (C::EXPAND) load_rect<G::IH, G::IW, G::IWS, NT>(Xs, xb, C::CIN, C::CIN, Hin, Win, iy0, ix0);
+    copy_f4<NT>(Ws, wts, C::CB);
+
+    float acc[C::IPT][C::PN3][4];
+#pragma unroll
+    for (int it = 0; it < C::IPT; ++it)
+#pragma unroll
+        for (int n = 0; n < C::PN3; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
+
+    for (int c = 0; c < C::NCHUNK; ++c) {
+        const float* Wc = Ws + (c & 1) * C::CB;
+        __syncthreads();   // chunk c weights (and Xs) visible; Es/Ds of chunk c-1 no longer read
+        if (c + 1 < C::NCHUNK) copy_f4<NT>(Ws + ((c + 1) & 1) * C::CB, wts + (size_t)(c + 1) * C::CB, C::CB);
+        if (C::EXPAND) {
+            float* sk = C::DUAL ? skip + ((size_t)t.b * C::CMID + c * C::MC) * Hin * Win : nullptr;
+            pw_halo<G, C::CIN, C::MC, C::PN1, NT, C::DUAL>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win,
+                                                           sk, C::CMID - c * C::MC);
+        } else {
+            load_rect<G::IH, G::IW, G::IWS, NT>(Es, xb + (size_t)c * C::MC * Hin * Win, C::MC, C::CIN - c * C::MC,
+                                                Hin, Win, iy0, ix0);
+        }
+        __syncthreads();
+        dw_stage<G, C::MC, C::RH, NT>(Es, Wc + C::OFF_WD, Wc + C::OFF_BD, Ds);
+        __syncthreads();
+        pw_accum<G::OPIX, C::MC, C::COUT, C::PN3, C::IPT, NT>(Ds, Wc + C::OFF_W2, acc);
+    }
+
+    const float* b2 = wts + C::OFF_B2;
+    if (C::HEADN > 0) __syncthreads();   // Ds/Es are about to be reused as the projected tile
+    float* Os = smem;                    // [COUT][OPIX] (HEADN > 0 only)
+#pragma unroll
+    for (int it = 0; it < C::IPT; ++it) {
+        const int item = threadIdx.x + it * NT;
+        if (item < C::NPG3 * C::NCG3) {
+            const int cg = item / C::NPG3;
+            const int pg = item - cg * C::NPG3;
+            const int p0 = pg * 4;
+            const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+            const int gy = oy0 + oy, gx0 = ox0 + ox;
+#pragma unroll
+            for (int n = 0; n < C::PN3; ++n) {
+                const int ch = cg * C::PN3 + n;
+                const float b = __ldg(b2 + ch);
+                float v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = acc[it][n][i] + b;
+                if (C::RES) {
+                    const float* xr = Xs + ch * G::IPIX + (oy + G::P) * G::IWS + ox + G::P;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] += xr[i];     // out += residual, no ReLU after (yolo_fastest.py:65)
+                }
+                if (C::RELU_OUT) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (C::HEADN > 0) {
+                    st4(Os + ch * G::OPIX + p0, make_float4(v[0], v[1], v[2], v[3]));
+                } else if (gy < Hout) {
+                    store_px4(y + (((size_t)t.b * C::COUT + ch) * Hout + gy) * Wout, gx0, Wout, v);
+                }
+            }
+        }
+    }
+    if (C::HEADN > 0) {
+        // biased 1x1 head conv (yolo_fastest.py:138,148) straight from the projected tile in smem;
+        // head weights [COUT][HEADP] are read through L1 (warp-broadcast).
+        __syncthreads();
+        const int headp = (headn + 3) & ~3;
+        const float* Wh = wts + C::OFF_WH;
+        const float* bh = Wh + C::COUT * headp;
+        constexpr int NPG = G::OPIX / 4;
+        const int NCGH = headp / 4;
+        for (int item = threadIdx.x; item < NPG * NCGH; item += NT) {
+            const int cg = item / NPG;
+            const int pg = item - cg * NPG;
+            const int p0 = pg * 4;
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bh + cg * 4));
+            float a[4][4] = {{bb.x, bb.x, bb.x, bb.x}, {bb.y, bb.y, bb.y, bb.y}, {bb.z, bb.z, bb.z, bb.z}, {bb.w, bb.w, bb.w, bb.w}};
+#pragma unroll 8
+            for (int k = 0; k < C::COUT; ++k) {
+                const float4 ov = ld4(Os + k * G::OPIX + p0);
+                const float4 w = __ldg(reinterpret_cast<const float4*>(Wh + k * headp + cg * 4));
+                const float o4[4] = {ov.x, ov.y, ov.z, ov.w};
+                const float w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[q][i] = fmaf(w4[q], o4[i], a[q][i]);
+            }
+            const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+            const int gy = oy0 + oy, gx0 = ox0 + ox;
+            if (gy < Hout) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ch = cg * 4 + q;
+                    if (ch < headn) store_px4(y + (((size_t)t.b * headn + ch) * Hout + gy) * Wout, gx0, Wout, a[q]);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem group: conv0 (dense 3x3 s2, in_ch=1 -> 8, ReLU) -> conv1_2 (1x1 8->8 ReLU) -> conv1_3 (dw3x3 ReLU)
+// -> conv1_4 (1x1 8->4 linear)   (yolo_fastest.py:78-82,151-154).  Input [B,1,H,W], output [B,4,H/2,W/2].
+// Packed weights: [W0: 9*8 ([tap][c])][b0: 8][W1: 8*8 ([k][m])][b1: 8][Wd: 8*9][bd: 8][W2: 8*4 ([m][n])][b2: 4]
+// With U8IN the input is uint8 and (x-128)/255 is applied on load (detect.py:123-124).
+// ---------------------------------------------------------------------------------------------
+template <int TH_, int TW_, int NT_, int MINB_>
+struct StemCfg {
+    static constexpr int NT = NT_, MINB = MINB_;
+    using G = Geo<3, 1, TH_, TW_>;
+    static constexpr int RH = 2 * G::IH + 1;          // raw input rows feeding the conv0 halo tile
+    static constexpr int RW = 2 * G::IWS + 1;
+    static constexpr int RWS = rup(RW, 4);
+    static constexpr int OFF_W0 = 0, OFF_B0 = 72, OFF_W1 = 80, OFF_B1 = 144, OFF_WD = 152, OFF_BD = 224, OFF_W2 = 232, OFF_B2 = 264;
+    static constexpr int WFLOATS = 268;
+    static constexpr int RS = RH * RWS;
+    static constexpr int XS = 8 * G::IPIX, ES = 8 * G::IPIX, DS = 8 * G::OPIX;
+    static constexpr int SMEM_FLOATS = RS + XS + ES + DS + WFLOATS;
+    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+    static constexpr int IPT = cdiv(G::OPIX / 4, NT);
+    static_assert(SMEM_BYTES <= 227 * 1024, "stem tile too large");
+};
+
+template <class C, bool U8IN>
+__global__ void __launch_bounds__(C::NT, C::MINB)
+stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __restrict__ wts,
+            int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y) {
+    using G = typename C::G;
+    constexpr int NT = C::NT;
+    extern __shared__ __align__(16) float smem[];
+    float* Rs = smem;
+    float* Xs = Rs + C::RS;
+    float* Es = Xs + C::XS;
+    float* Ds = Es + C::ES;
+    float* Ws = Ds + C::DS;
+    const TileId t = tile_id(tiles_x, tiles_y);
+    const int oy0 = t.ty * G::TH, ox0 = t.tx * G::TW;
+    const int iy0 = oy0 - 1, ix0 = ox0 - 1;            // halo origin in the H/2 map
+    const int ry0 = 2 * iy0 - 1, rx0 = 2 * ix0 - 1;    // raw origin (conv0: stride 2, pad 1)
+    // raw tile
+    for (int idx = threadIdx.x; idx < C::RS; idx += NT) {
+        const int r = idx / C::RWS, j = idx - r * C::RWS;
+        const int gy = ry0 + r, gx = rx0 + j;
+        float v = 0.f;
+        if (j < C::RW && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win) {
+            const size_t off = ((size_t)t.b * Hin + gy) * Win + gx;
+            if (U8IN) v = ((float)__ldg(reinterpret_cast<const unsigned char*>(xin) + off) - 128.0f) / 255.0f;
+            else v = __ldg(reinterpret_cast<const float*>(xin) + off);
+        }
+        Rs[idx] = v;
+    }
+    for (int i = threadIdx.x; i < C::WFLOATS; i += NT) Ws[i] = __ldg(wts + i);
+    __syncthreads();
+    // conv0 over the halo tile: item = 4 consecutive halo pixels x 8 channels
+    {
+        constexpr int NPG = G::IPIX / 4;
+        const float* W0 = Ws + C::OFF_W0;
+        for (int pg = threadIdx.x; pg < NPG; pg += NT) {
+            const int p0 = pg * 4;
+            const int r = p0 / G::IWS, j0 = p0 - r * G::IWS;
+            float a[8][4];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[c][i] = Ws[C::OFF_B0 + c];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                float v[9];
+                const float* rp = Rs + (2 * r + dy) * C::RWS + 2 * j0;
+                load_row<9>(v, rp);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float4 wa = ld4(W0 + (dy * 3 + dx) * 8);
+                    const float4 wb = ld4(W0 + (dy * 3 + dx) * 8 + 4);
+                    const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) a[c][i] = fmaf(w8[c], v[2 * i + dx], a[c][i]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                st4(Xs + c * G::IPIX + p0, make_float4(fmaxf(a[c][0], 0.f), fmaxf(a[c][1], 0.f), fmaxf(a[c][2], 0.f), fmaxf(a[c][3], 0.f)));
+        }
+    }
+    __syncthreads();
+    pw_halo<G, 8, 8, 8, NT, false>(Xs, Ws + C::OFF_W1, Ws + C::OFF_B1, Es, iy0, ix0, Hout, Wout, nullptr, 0);
+    __syncthreads();
+    dw_stage<G, 8, G::TH, NT>(Es, Ws + C::OFF_WD, Ws + C::OFF_BD, Ds);
+    __syncthreads();
+    float acc[C::IPT][4][4];
+#pragma unroll
+    for (int it = 0; it < C::IPT; ++it)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
+    pw_accum<G::OPIX, 8, 4, 4, C::IPT, NT>(Ds, Ws + C::OFF_W2, acc);
+#pragma unroll
+    for (int it = 0; it < C::IPT; ++it) {
+        const int pg = threadIdx.x + it * NT;
+        if (pg < G::OPIX / 4) {
+            const int p0 = pg * 4;
+            const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+            const int gy = oy0 + oy, gx0 = ox0 + ox;
+            if (gy < Hout) {
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float b = Ws[C::OFF_B2 + n];
+                    const float v[4] = {acc[it][n][0] + b, acc[it][n][1] + b, acc[it][n][2] + b, acc[it][n][3] + b};
+                    store_px4(y + (((size_t)t.b * 4 + n) * Hout + gy) * Wout, gx0, Wout, v);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense group: conv1_8 (1x1 4->24 ReLU) -> conv1_9 (dense 3x3 s2 24->24 ReLU) -> conv2_1 (1x1 24->8 linear)
+// (yolo_fastest.py:86-89,158-160).  22% of the network's MACs sit in conv1_9.
+// The 24 mid channels are processed in chunks of MC; conv1_9 accumulates in registers
+// (item = 4 output pixels x 8 output channels).
+// Packed weights: NCHUNK x { [W1: 4*MC][b1: MC][Wc: MC*3*3(dy)*(3 cg)*(3 dx * 8 n)] } then
+//                 [b9: 24][W3: 24*8 ([m][n])][b3: 8]
+// ---------------------------------------------------------------------------------------------
+template <int TH_, int TW_, int MC_, int NT_, int MINB_>
+struct DenseCfg {
+    static constexpr int NT = NT_, MINB = MINB_, MC = MC_;
+    using G = Geo<3, 2, TH_, TW_>;
+    static constexpr int CM = 24;
+    static constexpr int NCHUNK = CM / MC;
+    static constexpr int OFF_W1 = 0, OFF_B1 = 4 * MC, OFF_WC = OFF_B1 + MC;
+    static constexpr int CB = OFF_WC + MC * 3 * 3 * 24;          // [c][dy][cg][dx][8]
+    static constexpr int OFF_B9 = NCHUNK * CB, OFF_W3 = OFF_B9 + 24, OFF_B3 = OFF_W3 + 24 * 8;
+    static constexpr int WFLOATS = OFF_B3 + 8;
+    static constexpr int XS = 4 * G::IPIX, ES = MC * G::IPIX, DS = 24 * G::OPIX;
+    static constexpr int SMEM_FLOATS = XS + ES + DS + WFLOATS;
+    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+    static constexpr int NPG = G::OPIX / 4;
+    static constexpr int IPT9 = cdiv(NPG * 3, NT);     // conv1_9 items: px-groups x 3 channel groups of 8
+    static constexpr int IPT3 = cdiv(NPG * 2, NT);     // conv2_1 items: px-groups x 2 channel groups of 4
+    static_assert(CM % MC == 0 && MC % 4 == 0, "bad MC");
+    static_assert(SMEM_BYTES <= 227 * 1024, "dense tile too large");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB)
+dense_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts,
+             int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y) {
+    using G = typename C::G;
+    constexpr int NT = C::NT;
+    extern __shared__ __align__(16) float smem[];
+    float* Xs = smem;
+    float* Es = Xs + C::XS;
+    float* Ds = Es + C::ES;
+    float* Ws = Ds + C::DS;
+    const TileId t = tile_id(tiles_x, tiles_y);
+    const int oy0 = t.ty * G::TH, ox0 = t.tx * G::TW;
+    const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+    load_rect<G::IH, G::IW, G::IWS, NT>(Xs, x + (size_t)t.b * 4 * Hin * Win, 4, 4, Hin, Win, iy0, ix0);
+    copy_f4<NT>(Ws, wts, C::WFLOATS);
+
+    float acc[C::IPT9][8][4];
+#pragma unroll
+    for (int it = 0; it < C::IPT9; ++it)
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
+
+    for (int c = 0; c < C::NCHUNK; ++c) {
+        const float* Wc = Ws + c * C::CB;
+        __syncthreads();
+        pw_halo<G, 4, C::MC, 4, NT, false>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win, nullptr, 0);
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < C::IPT9; ++it) {
+            const int item = threadIdx.x + it * NT;
+            if (item < C::NPG * 3) {
+                const int cg = item / C::NPG;
+                const int pg = item - cg * C::NPG;
+                const int p0 = pg * 4;
+                const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+                const float* ep = Es + (oy * 2) * G::IWS + ox * 2;
+                const float* wp = Wc + C::OFF_WC + cg * 24;
+#pragma unroll 2
+                for (int m = 0; m < C::MC; ++m) {
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        float v[9];
+                        load_row<9>(v, ep + m * G::IPIX + dy * G::IWS);
+                        const float* w = wp + (m * 3 + dy) * 72;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float4 wa = ld4(w + dx * 8);
+                            const float4 wb = ld4(w + dx * 8 + 4);
+                            const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                            for (int n = 0; n < 8; ++n)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) acc[it][n][i] = fmaf(w8[n], v[2 * i + dx], acc[it][n][i]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // conv1_9 bias + ReLU -> Ds[24][OPIX]
+#pragma unroll
+    for (int it = 0; it < C::IPT9; ++it) {
+        const int item = threadIdx.x + it * NT;
+        if (item < C::NPG * 3) {
+            const int cg = item / C::NPG;
+            const int pg = item - cg * C::NPG;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const float b = Ws[C::OFF_B9 + cg * 8 + n];
+                st4(Ds + (cg * 8 + n) * G::OPIX + pg * 4,
+                    make_float4(fmaxf(acc[it][n][0] + b, 0.f), fmaxf(acc[it][n][1] + b, 0.f),
+                                fmaxf(acc[it][n][2] + b, 0.f), fmaxf(acc[it][n][3] + b, 0.f)));
+            }
+        }
+    }
+    __syncthreads();
+    float a3[C::IPT3][4][4];
+#pragma unroll
+    for (int it = 0; it < C::IPT3; ++it)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a3[it][n][i] = 0.f;
+    pw_accum<G::OPIX, 24, 8, 4, C::IPT3, NT>(Ds, Ws + C::OFF_W3, a3);
+#pragma unroll
+    for (int it = 0; it < C::IPT3; ++it) {
+        const int item = threadIdx.x + it * NT;
+        if (item < C::NPG * 2) {
+            const int cg = item / C::NPG;
+            const int pg = item - cg * C::NPG;
+            const int p0 = pg * 4;
+            const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+            const int gy = oy0 + oy, gx0 = ox0 + ox;
+            if (gy < Hout) {
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const int ch = cg * 4 + n;
+                    const float b = Ws[C::OFF_B3 + ch];
+                    const float v[4] = {a3[it][n][0] + b, a3[it][n][1] + b, a3[it][n][2] + b, a3[it][n][3] + b};
+                    store_px4(y + (((size_t)t.b * 8 + ch) * Hout + gy) * Wout, gx0, Wout, v);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plain 1x1 conv + bias (+ReLU) over a flat pixel tile (conv5_2, yolo_fastest.py:132,200).
+// Packed weights: [W: K*N ([k][n])][b: N]
+// ---------------------------------------------------------------------------------------------
+template <int K_, int N_, int PIXT_, int PN_, int NT_, bool RELU_>
+struct PwCfg {
+    static constexpr int K = K_, N = N_, PIXT = PIXT_, PN = PN_, NT = NT_;
+    static constexpr bool RELU = RELU_;
+    static constexpr int WFLOATS = K * N + N;
+    static constexpr int SMEM_FLOATS = K * PIXT + WFLOATS;
+    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+    static constexpr int IPT = cdiv((PIXT / 4) * (N / PN), NT);
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT)
+pw_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts, int HW, int tiles) {
+    constexpr int NT = C::NT;
+    extern __shared__ __align__(16) float smem[];
+    float* Xs = smem;
+    float* Ws = Xs + C::K * C::PIXT;
+    const int b = blockIdx.x / tiles;
+    const int p0t = (blockIdx.x - b * tiles) * C::PIXT;
+    const float* xb = x + (size_t)b * C::K * HW;
+    for (int idx = threadIdx.x; idx < C::K * C::PIXT; idx += NT) {
+        const int k = idx / C::PIXT, p = idx - k * C::PIXT;
+        Xs[idx] = (p0t + p < HW) ? __ldg(xb + (size_t)k * HW + p0t + p) : 0.f;
+    }
+    copy_f4<NT>(Ws, wts, C::WFLOATS);
+    __syncthreads();
+    float acc[C::IPT][C::PN][4];
+#pragma unroll
+    for (int it = 0; it < C::IPT; ++it)
+#pragma unroll
+        for (int n = 0; n < C::PN; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
+    pw_accum<C::PIXT, C::K, C::N, C::PN, C::IPT, NT>(Xs, Ws, acc);
+    constexpr int NPG = C::PIXT / 4;
+#pragma unroll
+    for (int it = 0; it < C::IPT; ++it) {
+        const int item = threadIdx.x + it * NT;
+        if (item < NPG * (C::N / C::PN)) {
+            const int cg = item / NPG;
+            const int pg = item - cg * NPG;
+#pragma unroll
+            for (int n = 0; n < C::PN; ++n) {
+                const int ch = cg * C::PN + n;
+                const float bsv = Ws[C::K * C::N + ch];
+                float v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[i] = acc[it][n][i] + bsv;
+                    if (C::RELU) v[i] = fmaxf(v[i], 0.f);
+                }
+                float* yp = y + ((size_t)b * C::N + ch) * HW;
+                const int p = p0t + pg * 4;
+                if (((HW & 3) == 0) && p + 3 < HW) st4(yp + p, make_float4(v[0], v[1], v[2], v[3]));
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (p + i < HW) yp[p + i] = v[i];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused upsample + concat + 1x1: deconv5_1 (ConvTranspose2d k2 s2 96->96 + BN + ReLU, yolo_fastest.py:42-48,140,208)
+// -> cat((conv4_2[136], deconv5_1[96]), 1) (:209) -> conv4_1_1 (1x1 232->96 + ReLU, :142).
+// The upsampled tensor and the concatenation never exist in memory: for each K-chunk the CTA either
+// stages 136-side skip channels or computes the 96 up-channels for its tile from the parent
+// (H/32) pixels, and accumulates the 1x1 into register tiles.
+// Packed weights: [Wa: 136*96 ([k][n])][Wb: 96*96 ([k][n])][b: 96]
+//                 [Wt: 2(py) * 96(c) * 96(m) * 2(px)][bt: 96]
+// ---------------------------------------------------------------------------------------------
+template <int TH_, int TW_, int KC_, int NT_, int MINB_>
+struct UpCatCfg {
+    static constexpr int TH = TH_, TW = TW_, KC = KC_, NT = NT_, MINB = MINB_;
+    static constexpr int CS = 136, CU = 96, N = 96;
+    static constexpr int OPIX = TH * TW, PH = TH / 2, PW = TW / 2, PPIX = PH * PW;
+    static constexpr int OFF_WA = 0, OFF_WB = CS * N, OFF_B = OFF_WB + CU * N, OFF_WT = OFF_B + N, OFF_BT = OFF_WT + 2 * CU * CU * 2;
+    static constexpr int WFLOATS = OFF_BT + CU;
+    static constexpr int PN = 8;
+    static constexpr int IPT = cdiv((OPIX / 4) * (N / PN), NT);
+    static constexpr int CSP = rup(CS, KC);
+    static constexpr int PS = CU * PPIX;            // parent tile [96][PPIX]
+    static constexpr int BS = KC * OPIX;            // K-chunk buffer
+    static constexpr int WS = KC * N;               // conv4_1_1 rows of the chunk
+    static constexpr int SMEM_FLOATS = PS + BS + WS;
+    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+    static_assert(TH % 2 == 0 && TW % 4 == 0 && CU % KC == 0 && KC % 8 == 0, "bad upcat tiling");
+    static_assert(SMEM_BYTES <= 227 * 1024, "upcat tile too large");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB)
+upcat_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __restrict__ low /*[B,96,H/2,W/2]*/,
+             float* __restrict__ y /*[B,96,H,W]*/, const float* __restrict__ wts, int H, int W, int tiles_x, int tiles_y) {
+    constexpr int NT = C::NT;
+    extern __shared__ __align__(16) float smem[];
+    float* Ps = smem;
+    float* Bs = Ps + C::PS;
+    float* Ws = Bs + C::BS;
+    const TileId t = tile_id(tiles_x, tiles_y);
+    const int oy0 = t.ty * C::TH, ox0 = t.tx * C::TW;
+    const int Hl = H / 2, Wl = W / 2;
+    // parent tile
+    for (int idx = threadIdx.x; idx < C::PS; idx += NT) {
+        const int c = idx / C::PPIX, p = idx - c * C::PPIX;
+        const int py = p / C::PW, px = p - py * C::PW;
+        const int gy = oy0 / 2 + py, gx = ox0 / 2 + px;
+        Ps[idx] = (gy < Hl && gx < Wl) ? __ldg(low + (((size_t)t.b * C::CU + c) * Hl + gy) * Wl + gx) : 0.f;
+    }
+    float acc[C::IPT][C::PN][4];
+#pragma unroll
+    for (int it = 0; it < C::IPT; ++it)
+#pragma unroll
+        for (int n = 0; n < C::PN; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
+
+    constexpr int NCH_S = C::CSP / C::KC, NCH_U = C::CU / C::KC;
+    for (int c = 0; c < NCH_S + NCH_U; ++c) {
+        __syncthreads();     // previous chunk fully consumed (and Ps visible)
+        if (c < NCH_S) {
+            // stage skip channels [c*KC, c*KC+KC) of the tile (zero beyond 136) + their conv4_1_1 rows
+            const int k0 = c * C::KC;
+            for (int idx = threadIdx.x; idx < C::BS; idx += NT) {
+                const int k = idx / C::OPIX, p = idx - k * C::OPIX;
+                const int oy = p / C::TW, ox = p - oy * C::TW;
+                const int gy = oy0 + oy, gx = ox0 + ox;
+                float v = 0.f;
+                if (k0 + k < C::CS && gy < H && gx < W) v = __ldg(skip + (((size_t)t.b * C::CS + k0 + k) * H + gy) * W + gx);
+                Bs[idx] = v;
+            }
+            for (int idx = threadIdx.x; idx < C::WS; idx += NT) {
+                const int k = idx / C::N;
+                Ws[idx] = (k0 + k < C::CS) ? __ldg(wts + C::OFF_WA + (size_t)k0 * C::N + idx) : 0.f;
+            }
+        } else {
+            // compute up channels [m0, m0+KC): U[m][q] = relu(sum_c Wt[py][c][m][px] * P[c][parent(q)] + bt[m])
+            const int m0 = (c - NCH_S) * C::KC;
+            copy_f4<NT>(Ws, wts + C::OFF_WB + (size_t)m0 * C::N, C::WS);
+            constexpr int NPG = C::OPIX / 4, NCG = C::KC / 8;
+            for (int item = threadIdx.x; item < NPG * NCG; item += NT) {
+                const int cg = item / NPG;
+                const int pg = item - cg * NPG;
+                const int p0 = pg * 4;
+                const int oy = p0 / C::TW, ox = p0 - oy * C::TW;
+                const int py = oy & 1;
+                const float* pp = Ps + (oy >> 1) * C::PW + (ox >> 1);
+                const float* wt = wts + C::OFF_WT + ((size_t)py * C::CU * C::CU + (m0 + cg * 8)) * 2;
+                float u[8][4];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const float b = __ldg(wts + C::OFF_BT + m0 + cg * 8 + n);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) u[n][i] = b;
+                }
+#pragma unroll 4
+                for (int k = 0; k < C::CU; ++k) {
+                    const float2 pv = *reinterpret_cast<const float2*>(pp + k * C::PPIX);
+                    const float* wk = wt + (size_t)k * C::CU * 2;
+#pragma unroll
+                    for (int n4 = 0; n4 < 4; ++n4) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(wk + n4 * 4));   // (m, px0) (m, px1) (m+1, px0) (m+1, px1)
+                        u[n4 * 2 + 0][0] = fmaf(w.x, pv.x, u[n4 * 2 + 0][0]);
+                        u[n4 * 2 + 0][1] = fmaf(w.y, pv.x, u[n4 * 2 + 0][1]);
+                        u[n4 * 2 + 0][2] = fmaf(w.x, pv.y, u[n4 * 2 + 0][2]);
+                        u[n4 * 2 + 0][3] = fmaf(w.y, pv.y, u[n4 * 2 + 0][3]);
+                        u[n4 * 2 + 1][0] = fmaf(w.z, pv.x, u[n4 * 2 + 1][0]);
+                        u[n4 * 2 + 1][1] = fmaf(w.w, pv.x, u[n4 * 2 + 1][1]);
+                        u[n4 * 2 + 1][2] = fmaf(w.z, pv.y, u[n4 * 2 + 1][2]);
+                        u[n4 * 2 + 1][3] = fmaf(w.w, pv.y, u[n4 * 2 + 1][3]);
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < 8; ++n)
+                    st4(Bs + (cg * 8 + n) * C::OPIX + p0,
+                        make_float4(fmaxf(u[n][0], 0.f), fmaxf(u[n][1], 0.f), fmaxf(u[n][2], 0.f), fmaxf(u[n][3], 0.f)));
+            }
+        }
+        __syncthreads();
+        pw_accum<C::OPIX, C::KC, C::N, C::PN, C::IPT, NT>(Bs, Ws, acc);
+    }
+    constexpr int NPG = C::OPIX / 4;
+#pragma unroll
+    for (int it = 0; it < C::IPT; ++it) {
+        const int item = threadIdx.x + it * NT;
+        if (item < NPG * (C::N / C::PN)) {
+            const int cg = item / NPG;
+            const int pg = item - cg * NPG;
+            const int p0 = pg * 4;
+            const int oy = p0 / C::TW, ox = p0 - oy * C::TW;
+            const int gy = oy0 + oy, gx0 = ox0 + ox;
+            if (gy < H) {
+#pragma unroll
+                for (int n = 0; n < C::PN; ++n) {
+                    const int ch = cg * C::PN + n;
+                    const float b = __ldg(wts + C::OFF_B + ch);
+                    const float v[4] = {fmaxf(acc[it][n][0] + b, 0.f), fmaxf(acc[it][n][1] + b, 0.f),
+                                        fmaxf(acc[it][n][2] + b, 0.f), fmaxf(acc[it][n][3] + b, 0.f)};
+                    store_px4(y + (((size_t)t.b * C::N + ch) * H + gy) * W, gx0, W, v);
+                }
+            }
+        }
+    }
+}
+
+// u8 -> (x - 128) / 255 fp32 (detect.py:123-124) for callers that want the normalised tensor itself.
+__global__ void u8_normalize_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = ((float)src[i] - 128.0f) / 255.0f;
+}
+
+}  // namespace yf

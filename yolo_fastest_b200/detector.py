@@ -1,0 +1,267 @@
+"""Drop-ins for the reference detection driver (src/detect.py:14-192).
+
+``YOLO_post_process`` and ``Detect_YOLO`` keep the reference's constructor arguments, method names
+(including the spelling ``non_maxium_supression``) and return types — lists of
+``[x1, y1, x2, y2, conf, cls_score, cls_index]`` with Python-int coordinates — while every number is
+produced by libyf_b200.so on the GPU.  The batched entry points (``postprocess_batch``,
+``Detect_YOLO.detect_batch``) are what the reference's per-image Python loops turn into at B > 1.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import YoloFastest
+
+
+def _rows_from_dets(dets):
+    """structured array of yf_det -> the reference's list-of-lists rows (detect.py:65-66)."""
+    return [[int(d["x1"]), int(d["y1"]), int(d["x2"]), int(d["y2"]), float(d["conf"]), float(d["cls_score"]),
+             int(d["cls"])] for d in dets]
+
+
+class YOLO_post_process:
+    def __init__(self, conf_thres, nms_thres, num_anchors, num_class, anchors, input_shape):
+        self.conf_thres = conf_thres
+        self.nms_thres = nms_thres
+        self.num_anchors = num_anchors
+        self.num_class = num_class
+        self.bbox_attrs = 5 + num_class
+        self.anchors = anchors
+        self.input_shape = input_shape
+        self._ctx = None
+
+    # ---- plumbing ----------------------------------------------------------------------------
+    def _context(self, device, batch):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        H, W = self.input_shape[0], self.input_shape[1]
+        c = self._ctx
+        if c is None or c.device_index != idx or c.max_batch < batch:
+            if c is not None:
+                torch.cuda.synchronize(c.device_index)
+                c.close()
+            with torch.cuda.device(idx):
+                c = _lib.Ctx(idx, 1, self.num_class, self.num_anchors, batch, H, W)
+            self._ctx = c
+        return c
+
+    def _params(self, mode, max_det, conf_thres=None):
+        return _lib.make_params(self.anchors, self.conf_thres if conf_thres is None else conf_thres, self.nms_thres,
+                                self.input_shape[0], self.input_shape[1], mode, max_det)
+
+    @staticmethod
+    def _to_cuda(t):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t))
+        if not t.is_cuda:
+            if not torch.cuda.is_available():
+                raise _lib.YfError("post-processing runs on the GPU only (no CPU fallback) and no CUDA device is available")
+            t = t.cuda()
+        return t.contiguous().float()
+
+    def _run(self, pred, nms, mode=_lib.MODE_DETECT, max_det=None):
+        hl, hs = self._to_cuda(pred[0]), self._to_cuda(pred[1])
+        B = hl.shape[0]
+        if hl.shape[1] != self.num_anchors * self.bbox_attrs or hs.shape[1] != hl.shape[1] or hs.shape[0] != B:
+            raise _lib.YfError("head shapes %s / %s do not match %d anchors x %d attrs"
+                               % (tuple(hl.shape), tuple(hs.shape), self.num_anchors, self.bbox_attrs))
+        ctx = self._context(hl.device, B)
+        ncand = self.num_anchors * (hl.shape[2] * hl.shape[3] + hs.shape[2] * hs.shape[3])
+        max_det = ncand if max_det is None else max_det
+        out = torch.empty((B, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8, device=hl.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=hl.device)
+        status = torch.empty((B,), dtype=torch.int32, device=hl.device)
+        p = self._params(mode, max_det)
+        fn = _lib.lib().yf_postprocess if nms else _lib.lib().yf_decode
+        stream = torch.cuda.current_stream(hl.device).cuda_stream
+        with torch.cuda.device(hl.device):
+            _lib.check(fn(ctx.handle, hl.data_ptr(), hs.data_ptr(), B, hl.shape[2], hl.shape[3], hs.shape[2], hs.shape[3],
+                          C.byref(p), out.data_ptr(), counts.data_ptr(), status.data_ptr(), C.c_void_p(stream)), ctx.handle)
+        counts_h = counts.cpu().numpy()
+        status_h = status.cpu().numpy()
+        dets = out.cpu().numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
+        return [dets[b, :min(int(counts_h[b]), max_det)] for b in range(B)], counts_h, status_h
+
+    # ---- reference API (detect.py:41-84) --------------------------------------------------------
+    def decode_box(self, pred):
+        """Candidates of batch element 0 with conf > conf_thres, in the reference's visiting order."""
+        dets, _, _ = self._run((pred[0][0:1], pred[1][0:1]), nms=False)
+        return _rows_from_dets(dets[0])
+
+    def non_maxium_supression(self, bbox_list):
+        """Greedy NMS of one class's list, already sorted by conf descending; returns the kept rows."""
+        n = len(bbox_list)
+        if n == 0:
+            return []
+        if not torch.cuda.is_available():
+            raise _lib.YfError("NMS runs on the GPU only (no CPU fallback) and no CUDA device is available")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ctx = self._context(dev, 1)
+        boxes = torch.tensor([[int(b[0]), int(b[1]), int(b[2]), int(b[3])] for b in bbox_list], dtype=torch.int32, device=dev)
+        keep = torch.empty((n,), dtype=torch.int32, device=dev)
+        n_keep = torch.zeros((1,), dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().yf_nms_sorted_i32(ctx.handle, boxes.data_ptr(), n, float(self.nms_thres), keep.data_ptr(),
+                                                   n_keep.data_ptr(), C.c_void_p(stream)), ctx.handle)
+        k = int(n_keep.item())
+        return [bbox_list[i] for i in keep[:k].cpu().tolist()]
+
+    # ---- batched form ------------------------------------------------------------------------------
+    def decode_box_batch(self, pred):
+        dets, _, _ = self._run(pred, nms=False)
+        return [_rows_from_dets(d) for d in dets]
+
+    def postprocess_batch(self, pred, max_det=None, raw=False):
+        """decode -> class split -> stable sort -> per-class NMS for every image (detect.py:155-169).
+        Returns one list of rows per image (or the structured arrays with ``raw=True``)."""
+        dets, counts, status = self._run(pred, nms=True, max_det=max_det)
+        if (status & 1).any():
+            raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
+        return dets if raw else [_rows_from_dets(d) for d in dets]
+
+
+def plot_one_box(xyxy, img, color=None, label=None, line_thickness=None):
+    """Draw one labelled box (same look as the reference helper, utils/general.py:56-67). Host-side, cv2."""
+    import cv2
+    tl = line_thickness or round(0.002 * (img.shape[0] + img.shape[1]) / 2) + 1
+    color = color or [int(v) for v in np.random.randint(0, 255, 3)]
+    c1, c2 = (int(xyxy[0]), int(xyxy[1])), (int(xyxy[2]), int(xyxy[3]))
+    cv2.rectangle(img, c1, c2, color, thickness=tl, lineType=cv2.LINE_AA)
+    if label:
+        tf = min(tl - 1, 2)
+        t_size = cv2.getTextSize(label, fontFace=0, fontScale=tl / 5, thickness=tf)[0]
+        c2 = c1[0] + t_size[0], c1[1] - t_size[1] - 3
+        cv2.rectangle(img, c1, c2, color, thickness=-1, lineType=cv2.LINE_AA)
+        cv2.putText(img, label, (c1[0], c1[1] - 2), 0, tl / 5, [225, 255, 255], thickness=tf, lineType=cv2.LINE_AA)
+
+
+class Detect_YOLO:
+    def __init__(self, device, model_path, config_params, logger):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.YfError("Detect_YOLO of the B200 path needs a CUDA device (no CPU fallback), got %s" % device)
+        io = config_params["io_params"]
+        self.model = YoloFastest(io).to(device).eval()
+        net_param = torch.load(model_path, map_location="cpu")
+        self.model.load_state_dict(net_param)
+        self.logger = logger
+        self.device = device
+        self.class_names = io["class_names"]
+        self.num_cls = io["num_cls"]
+        self.nms_thres = io["nms_thre"]
+        self.conf_thres = io["conf_thre"]
+        self.input_shape = io["input_shape"]
+        self.origin_img_shape = io["origin_img_shape"]
+        self.post_process = YOLO_post_process(conf_thres=self.conf_thres, nms_thres=self.nms_thres,
+                                              num_anchors=io["num_anchors"], anchors=io["anchors"],
+                                              input_shape=self.input_shape, num_class=self.num_cls)
+        self.colors = [[106, 90, 205], [199, 97, 20], [112, 128, 105]]
+        self._pinned = {}
+
+    # ---- host-side image handling (unchanged semantics, detect.py:107-139) ------------------------
+    def _load_gray(self, img_path):
+        import cv2
+        ori_img = cv2.imread(img_path)
+        if self.input_shape[2] == 1 and self.origin_img_shape[2] != 1:
+            img = cv2.cvtColor(ori_img, cv2.COLOR_BGR2GRAY)
+        else:
+            img = ori_img
+        if list(self.input_shape[0:2]) != list(self.origin_img_shape[0:2]):
+            img = cv2.resize(img, (self.input_shape[1], self.input_shape[0]))
+        if img.ndim != 2:
+            raise _lib.YfError("the B200 path serves the single-channel models (input_shape[2] == 1)")
+        return np.ascontiguousarray(img), ori_img
+
+    def pre_process(self, img_path):
+        """imread -> gray -> resize -> (x - 128) / 255 -> [1, 1, H, W] on the device (detect.py:107-129)."""
+        u8, ori_img = self._load_gray(img_path)
+        img = torch.from_numpy(u8[None]).to(self.device).float()
+        img = (img - 128.0) / 255.0
+        return img.unsqueeze(0), ori_img
+
+    def adjust_coord(self, rows):
+        """round(coord * origin/input) in place, after NMS (detect.py:131-139)."""
+        scale_h = self.origin_img_shape[0] / self.input_shape[0]
+        scale_w = self.origin_img_shape[1] / self.input_shape[1]
+        for r in rows:
+            r[0] = round(r[0] * scale_w)
+            r[2] = round(r[2] * scale_w)
+            r[1] = round(r[1] * scale_h)
+            r[3] = round(r[3] * scale_h)
+
+    # ---- batched detection through the C ABI with host buffers -----------------------------------------
+    def detect_batch(self, u8_batch, max_det=64, raw=False):
+        """uint8 gray images [B, H, W] (host, network input size) -> per-image detection rows.
+
+        One yf_detect_host_u8 call: H2D copy of the bytes, fused normalisation + forward + decode +
+        NMS, D2H copy of the fixed-capacity result slab.  This is the end-to-end call bench.py times."""
+        u8_batch = np.ascontiguousarray(u8_batch, dtype=np.uint8)
+        B, H, W = u8_batch.shape
+        if [H, W] != list(self.input_shape[0:2]):
+            raise _lib.YfError("images are %dx%d, the network input is %s" % (H, W, self.input_shape[0:2]))
+        ctx = self.model.context(self.device, H, W, B)
+        key = (B, max_det)
+        if key not in self._pinned:
+            self._pinned = {key: (torch.empty((B, H, W), dtype=torch.uint8).pin_memory(),
+                                  torch.empty((B, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8).pin_memory(),
+                                  torch.empty((B,), dtype=torch.int32).pin_memory(),
+                                  torch.empty((B,), dtype=torch.int32).pin_memory())}
+        pin_in, pin_out, pin_cnt, pin_st = self._pinned[key]
+        pin_in.numpy()[...] = u8_batch
+        p = self.post_process._params(_lib.MODE_DETECT, max_det)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().yf_detect_host_u8(ctx.handle, pin_in.data_ptr(), B, C.byref(p), pin_out.data_ptr(),
+                                                   pin_cnt.data_ptr(), pin_st.data_ptr(), C.c_void_p(stream)), ctx.handle)
+        counts = pin_cnt.numpy()
+        if (pin_st.numpy() & 1).any():
+            raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
+        dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
+        res = [dets[b, :min(int(counts[b]), max_det)].copy() for b in range(B)]
+        return res if raw else [_rows_from_dets(d) for d in res]
+
+    # ---- reference driver (detect.py:141-192) ------------------------------------------------------------
+    def batch_detect(self, data_path, result_path):
+        import cv2
+        with torch.no_grad():
+            img_list = os.listdir(data_path)
+            num = len(img_list)
+            avg_time = 0
+            for filename in img_list:
+                img_path = os.path.join(data_path, filename)
+                img, ori_img = self.pre_process(img_path)
+
+                torch.cuda.synchronize(self.device)
+                start_time = time.time()
+                pred = self.model(img)
+                torch.cuda.synchronize(self.device)     # the reference omits this, so its GPU numbers would be launch times
+                time_mark = time.time()
+                infer_time = float(time_mark - start_time) * 1000
+
+                all_bbox_rects = self.post_process.postprocess_batch(pred)[0]
+                post_process_time = float(time.time() - time_mark) * 1000
+                total_time = infer_time + post_process_time
+                avg_time += total_time
+
+                if len(all_bbox_rects) == 0:
+                    cv2.imwrite(os.path.join(result_path, 'result_' + filename), ori_img)
+                    self.logger.info("image_name:%s -> no targets, infer time:%.2fms, post_process time:%.2fms, total time:%.2fms"
+                                     % (filename, infer_time, post_process_time, total_time))
+                    continue
+
+                if list(self.input_shape[0:2]) != list(self.origin_img_shape[0:2]):
+                    self.adjust_coord(all_bbox_rects)
+
+                for *xyxy, conf, cls_score, cls_pred in all_bbox_rects:
+                    label = '%s %.2f' % (self.class_names[int(cls_pred)], conf * cls_score)
+                    plot_one_box(xyxy, ori_img, label=label, color=self.colors[int(cls_pred)], line_thickness=3)
+
+                cv2.imwrite(os.path.join(result_path, 'result_' + filename), ori_img)
+                self.logger.info("image_name:%s -> detect finished, infer time:%.2fms, post_process time:%.2fms, total time:%.2fms"
+                                 % (filename, infer_time, post_process_time, total_time))
+
+            self.logger.info("detect avg_time: %.2fms" % (avg_time / num))

@@ -1,0 +1,245 @@
+"""Drop-in for the reference model class (src/model_training/model/yolo_fastest.py:69-231).
+
+``YoloFastest(io_params)`` keeps the reference's constructor, attribute names and state_dict keys
+(508 entries, e.g. ``res2_1.conv2.0.weight``, ``conv0.1.running_var``, ``head_5.bias``), so
+``load_state_dict(torch.load("models/pytorch/.../YOLO-Fastest_epoch_28.pth"))`` works unchanged
+(detect.py:89-91).  The parameters are held in ordinary ``nn`` modules only as storage: ``forward``
+folds BatchNorm on the host (fp64), hands the packed fp32 blob to libyf_b200.so once, and from then
+on every call is ``yf_forward`` — hand-written sm_100a kernels, no PyTorch operator on the path.
+There is no CPU or eager fallback: a CPU tensor, training mode or a missing library raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+BN_EPS = 1e-5
+
+# (attribute, kind, cin, cout, kernel, stride, depthwise, relu) in forward order (yolo_fastest.py:78-148).
+# kind: "cbr" conv+BN(+ReLU) Sequential, "res" BasicResBlock(io, inner), "head" biased 1x1 conv, "up" deconv+BN+ReLU
+ARCH = [
+    ("conv0", "cbr", None, 8, 3, 2, False, True),
+    ("conv1_2", "cbr", 8, 8, 1, 1, False, True),
+    ("conv1_3", "cbr", 8, 8, 3, 1, True, True),
+    ("conv1_4", "cbr", 8, 4, 1, 1, False, False),
+    ("res1_1", "res", 4, 8, 0, 0, False, False),
+    ("conv1_8", "cbr", 4, 24, 1, 1, False, True),
+    ("conv1_9", "cbr", 24, 24, 3, 2, False, True),
+    ("conv2_1", "cbr", 24, 8, 1, 1, False, False),
+    ("res2_1", "res", 8, 32, 0, 0, False, False),
+    ("res2_2", "res", 8, 32, 0, 0, False, False),
+    ("conv2_2", "cbr", 8, 32, 1, 1, False, True),
+    ("conv2_3", "cbr", 32, 32, 3, 2, True, True),
+    ("conv3_1", "cbr", 32, 8, 1, 1, False, False),
+    ("res3_1", "res", 8, 48, 0, 0, False, False),
+    ("res3_2", "res", 8, 48, 0, 0, False, False),
+    ("conv3_2", "cbr", 8, 48, 1, 1, False, True),
+    ("conv3_3", "cbr", 48, 48, 3, 1, True, True),
+    ("conv3_4", "cbr", 48, 16, 1, 1, False, False),
+    ("res3_3", "res", 16, 96, 0, 0, False, False),
+    ("res3_4", "res", 16, 96, 0, 0, False, False),
+    ("res3_5", "res", 16, 96, 0, 0, False, False),
+    ("res3_6", "res", 16, 96, 0, 0, False, False),
+    ("conv3_5", "cbr", 16, 96, 1, 1, False, True),
+    ("conv3_6", "cbr", 96, 96, 3, 2, True, True),
+    ("conv4_1", "cbr", 96, 24, 1, 1, False, False),
+    ("res4_1", "res", 24, 136, 0, 0, False, False),
+    ("res4_2", "res", 24, 136, 0, 0, False, False),
+    ("res4_3", "res", 24, 136, 0, 0, False, False),
+    ("res4_4", "res", 24, 136, 0, 0, False, False),
+    ("conv4_2", "cbr", 24, 136, 1, 1, False, True),
+    ("conv4_3", "cbr", 136, 136, 3, 2, True, True),
+    ("conv5_1", "cbr", 136, 48, 1, 1, False, True),
+    ("res5_1", "res", 48, 224, 0, 0, False, False),
+    ("res5_2", "res", 48, 224, 0, 0, False, False),
+    ("res5_3", "res", 48, 224, 0, 0, False, False),
+    ("res5_4", "res", 48, 224, 0, 0, False, False),
+    ("res5_5", "res", 48, 224, 0, 0, False, False),
+    ("conv5_2", "cbr", 48, 96, 1, 1, False, True),
+    ("conv5_3", "cbr", 96, 96, 5, 1, True, True),
+    ("conv5_4", "cbr", 96, 128, 1, 1, False, False),
+    ("conv5_5", "cbr", 128, 128, 5, 1, True, True),
+    ("conv5_6", "cbr", 128, 128, 1, 1, False, False),
+    ("head_5", "head", 128, None, 1, 1, False, False),
+    ("deconv5_1", "up", 96, 96, 2, 2, False, True),
+    ("conv4_1_1", "cbr", 232, 96, 1, 1, False, True),
+    ("conv4_1_2", "cbr", 96, 96, 5, 1, True, True),
+    ("conv4_1_3", "cbr", 96, 96, 1, 1, False, False),
+    ("conv4_1_4", "cbr", 96, 96, 5, 1, True, True),
+    ("conv4_1_5", "cbr", 96, 96, 1, 1, False, False),
+    ("head_4", "head", 96, None, 1, 1, False, False),
+]
+
+
+def _cbr(cin, cout, k, stride, depthwise, relu):
+    layers = [nn.Conv2d(cin, cout, k, stride, (k - 1) // 2, groups=cin if depthwise else 1, bias=False),
+              nn.BatchNorm2d(cout)]
+    if relu:
+        layers.append(nn.ReLU(inplace=False))
+    return nn.Sequential(*layers)
+
+
+class BasicResBlock(nn.Module):
+    """Parameter container with the reference block's attribute names (yolo_fastest.py:52-58)."""
+
+    def __init__(self, io_channels, inner_channels):
+        super().__init__()
+        self.conv1 = _cbr(io_channels, inner_channels, 1, 1, False, True)
+        self.conv2 = _cbr(inner_channels, inner_channels, 3, 1, True, True)
+        self.conv3 = _cbr(inner_channels, io_channels, 1, 1, False, False)
+
+    def forward(self, x):
+        raise _lib.YfError("BasicResBlock is a parameter container; the block runs fused inside yf_forward")
+
+
+def _fold(conv_w, bn, transposed=False):
+    """Eval-mode BN folded into the conv in fp64: w' = w*g/sqrt(v+eps), b' = beta - mean*g/sqrt(v+eps)."""
+    w = conv_w.detach().double().cpu()
+    g, b = bn.weight.detach().double().cpu(), bn.bias.detach().double().cpu()
+    m, v = bn.running_mean.detach().double().cpu(), bn.running_var.detach().double().cpu()
+    s = g / torch.sqrt(v + bn.eps)
+    w = w * (s.view(1, -1, 1, 1) if transposed else s.view(-1, 1, 1, 1))
+    return w.float().numpy().ravel(), (b - m * s).float().numpy().ravel()
+
+
+class YoloFastest(nn.Module):
+    def __init__(self, io_params):
+        super().__init__()
+        self.num_cls = io_params["num_cls"]
+        self.input_channel = io_params["input_channel"]
+        self.num_anchors = io_params["num_anchors"]
+        self.num_out = self.num_anchors * (5 + self.num_cls)
+        for name, kind, cin, cout, k, s, dw, relu in ARCH:
+            if kind == "cbr":
+                mod = _cbr(self.input_channel if cin is None else cin, cout, k, s, dw, relu)
+            elif kind == "res":
+                mod = BasicResBlock(cin, cout)
+            elif kind == "head":
+                mod = nn.Conv2d(cin, self.num_out, kernel_size=1, stride=1)
+            else:
+                mod = nn.Sequential(nn.ConvTranspose2d(cin, cout, kernel_size=k, stride=s, padding=0, bias=False),
+                                    nn.BatchNorm2d(cout), nn.ReLU())
+            setattr(self, name, mod)
+        self._ctx = None          # _lib.Ctx for the current (device, H, W, max_batch)
+        self._dirty = True        # packed weights on the device are stale
+
+    # ---- parameter bookkeeping -------------------------------------------------------------
+    def initialize_weights(self):
+        """Same initialisation as the reference (yolo_fastest.py:220-231)."""
+        for m in self.modules():
+            if type(m) is nn.Conv2d:
+                nn.init.kaiming_normal_(m.weight.data, nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif type(m) is nn.BatchNorm2d:
+                m.weight.data.normal_(1.0, 0.02)
+                m.bias.data.fill_(0)
+        self._dirty = True
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._dirty = True
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._dirty = True
+        return out
+
+    def refresh(self):
+        """Call after mutating parameters in place; the next forward re-folds and re-uploads them."""
+        self._dirty = True
+
+    def folded_blob(self):
+        """BN-folded fp32 parameters in the order yf_load_weights expects (include/yf.h)."""
+        parts = []
+        for name, kind, *_ in ARCH:
+            mod = getattr(self, name)
+            if kind == "cbr":
+                parts.extend(_fold(mod[0].weight, mod[1]))
+            elif kind == "res":
+                for sub in (mod.conv1, mod.conv2, mod.conv3):
+                    parts.extend(_fold(sub[0].weight, sub[1]))
+            elif kind == "head":
+                parts.append(mod.weight.detach().float().cpu().numpy().ravel())
+                parts.append(mod.bias.detach().float().cpu().numpy().ravel())
+            else:
+                parts.extend(_fold(mod[0].weight, mod[1], transposed=True))
+        blob = np.concatenate(parts).astype(np.float32)
+        expect = _lib.lib().yf_weight_count(self.input_channel, self.num_cls, self.num_anchors)
+        if blob.size != expect:
+            raise _lib.YfError("folded blob has %d floats, library expects %d" % (blob.size, expect))
+        return blob
+
+    # ---- execution ---------------------------------------------------------------------------
+    def context(self, device, H, W, batch):
+        """The yf_ctx serving (device, H, W); grown (re-created) when a larger batch arrives."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        c = self._ctx
+        if c is None or c.device_index != idx or c.H != H or c.W != W or c.max_batch < batch:
+            if c is not None:
+                torch.cuda.synchronize(c.device_index)
+                c.close()
+            with torch.cuda.device(idx):
+                c = _lib.Ctx(idx, self.input_channel, self.num_cls, self.num_anchors, batch, H, W)
+            self._ctx = c
+            self._dirty = True
+        if self._dirty:
+            with torch.cuda.device(idx):
+                torch.cuda.synchronize(idx)
+                c.load_weights(self.folded_blob())
+            self._dirty = False
+        return c
+
+    def _check_input(self, x):
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise _lib.YfError("YoloFastest.forward runs only on CUDA tensors (no CPU fallback); got %s"
+                               % (x.device if isinstance(x, torch.Tensor) else type(x)))
+        if self.training:
+            raise _lib.YfError("the B200 path is inference-only (BatchNorm is folded): call .eval() first")
+        if x.dim() != 4 or x.shape[1] != self.input_channel:
+            raise _lib.YfError("expected input [B, %d, H, W], got %s" % (self.input_channel, tuple(x.shape)))
+        if x.shape[2] % 32 or x.shape[3] % 32:
+            raise _lib.YfError("H and W must be multiples of 32 (_config.py:11), got %dx%d" % (x.shape[2], x.shape[3]))
+
+    def forward(self, x):
+        """[B, C, H, W] fp32 cuda -> (head_large [B, A(5+nc), H/16, W/16], head_small [.., H/32, W/32])."""
+        self._check_input(x)
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        ctx = self.context(x.device, H, W, B)
+        head_large = torch.empty((B, self.num_out, H // 16, W // 16), dtype=torch.float32, device=x.device)
+        head_small = torch.empty((B, self.num_out, H // 32, W // 32), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().yf_forward(ctx.handle, x.data_ptr(), B, head_large.data_ptr(), head_small.data_ptr(),
+                                             C.c_void_p(stream)), ctx.handle)
+        return head_large, head_small
+
+    def tap(self, name, batch):
+        """Intermediate activation ``name`` of the last forward (parity/debug aid; see yf_tap)."""
+        ctx = self._ctx
+        per = C.c_int64(0)
+        _lib.check(_lib.lib().yf_tap(ctx.handle, name.encode(), batch, None, C.byref(per), None), ctx.handle)
+        out = torch.empty((batch, per.value), dtype=torch.float32, device="cuda:%d" % ctx.device_index)
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        _lib.check(_lib.lib().yf_tap(ctx.handle, name.encode(), batch, out.data_ptr(), C.byref(per), C.c_void_p(stream)), ctx.handle)
+        return out
+
+    def profile(self, x):
+        """Per-group device milliseconds of one forward (yf_profile_forward)."""
+        self._check_input(x)
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        ctx = self.context(x.device, H, W, B)
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        torch.cuda.synchronize(x.device)
+        with torch.cuda.device(x.device):
+            n = _lib.lib().yf_profile_forward(ctx.handle, x.data_ptr(), B, names, ms, 64)
+        if n < 0:
+            _lib.check(n, ctx.handle)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
