@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the YOLO-Fastest detection hot path (forward + decode + confidence filter + per-class NMS).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--res 512x640|256x320] [--batch B]
+
+One step = one pass of the hot path over one batch of synthetic images per GPU.  Default workload
+(BASELINE.json metric): 640x512 images, batch 256 per GPU, the shipped 512x640 checkpoint.  Weak scaling:
+every rank processes its own batch; per-rank detection slabs are gathered to rank 0 with one NCCL gather.
+
+Prints ONE JSON line on rank 0:
+  value     images/s, whole job, inputs resident in HBM (yf_detect on device tensors)
+  e2e       images/s through the public API with HOST buffers (Detect_YOLO.detect_batch -> yf_detect_host_u8):
+            pinned uint8 images H2D, fused normalise+forward+decode+NMS, detection slab D2H, every step
+  roofline  dominant kernel (largest share of the step): algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  fp32      the same kernel's algorithmic FLOP/s vs the FP32 CUDA-core peak (the fused kernels are FP32-compute bound)
+  cpu_baseline  the oracle port of the reference (PyTorch CPU forward + the reference's Python decode/NMS loops)
+                timed on this box's host cores on a bounded sample (rank 0, N=1 only)
+--impl reference times that CPU port alone, with all host threads, on the same workload definition.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+METRIC = "images/sec at 640x512 b256, 1/2/4/8 B200; % HBM roofline per kernel"
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x max SM clock = 74.4
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work per fused group (per image): MACs, unique fp32 elements in/out, folded weights
+# ---------------------------------------------------------------------------------------------
+def group_work(H, W, nout):
+    px = lambda d: (H // d) * (W // d)
+    def pw(cin, cout, d): return px(d) * cin * cout, cin * cout + cout
+    def dw(c, k, d): return px(d) * c * k * k, c * k * k + c
+    def dense(cin, cout, k, d): return px(d) * cin * cout * k * k, cin * cout * k * k + cout
+    def irb(io, mid, d): return [pw(io, mid, d), dw(mid, 3, d), pw(mid, io, d)]
+    G = []
+    def add(name, layers, ins, outs):
+        macs = sum(l[0] for l in layers)
+        wts = sum(l[1] for l in layers)
+        G.append({"name": name, "macs": macs, "bytes": 4 * (sum(c * px(d) for c, d in ins) + sum(c * px(d) for c, d in outs) + wts)})
+    add("conv1_4", [dense(1, 8, 3, 2), pw(8, 8, 2), dw(8, 3, 2), pw(8, 4, 2)], [(1, 1)], [(4, 2)])
+    add("res1_1", irb(4, 8, 2), [(4, 2)], [(4, 2)])
+    add("conv2_1", [pw(4, 24, 2), dense(24, 24, 3, 4), pw(24, 8, 4)], [(4, 2)], [(8, 4)])
+    add("res2_1", irb(8, 32, 4), [(8, 4)], [(8, 4)])
+    add("res2_2", irb(8, 32, 4), [(8, 4)], [(8, 4)])
+    add("conv3_1", [pw(8, 32, 4), dw(32, 3, 8), pw(32, 8, 8)], [(8, 4)], [(8, 8)])
+    add("res3_1", irb(8, 48, 8), [(8, 8)], [(8, 8)])
+    add("res3_2", irb(8, 48, 8), [(8, 8)], [(8, 8)])
+    add("conv3_4", [pw(8, 48, 8), dw(48, 3, 8), pw(48, 16, 8)], [(8, 8)], [(16, 8)])
+    for n in ("res3_3", "res3_4", "res3_5", "res3_6"):
+        add(n, irb(16, 96, 8), [(16, 8)], [(16, 8)])
+    add("conv4_1", [pw(16, 96, 8), dw(96, 3, 16), pw(96, 24, 16)], [(16, 8)], [(24, 16)])
+    for n in ("res4_1", "res4_2", "res4_3", "res4_4"):
+        add(n, irb(24, 136, 16), [(24, 16)], [(24, 16)])
+    add("conv5_1", [pw(24, 136, 16), dw(136, 3, 32), pw(136, 48, 32)], [(24, 16)], [(136, 16), (48, 32)])
+    for n in ("res5_1", "res5_2", "res5_3", "res5_4", "res5_5"):
+        add(n, irb(48, 224, 32), [(48, 32)], [(48, 32)])
+    add("conv5_2", [pw(48, 96, 32)], [(48, 32)], [(96, 32)])
+    add("conv5_4", [dw(96, 5, 32), pw(96, 128, 32)], [(96, 32)], [(128, 32)])
+    add("head_5", [dw(128, 5, 32), pw(128, 128, 32), pw(128, nout, 32)], [(128, 32)], [(nout, 32)])
+    add("conv4_1_1", [(px(16) * 96 * 96, 96 * 96 * 4 + 96), pw(232, 96, 16)], [(136, 16), (96, 32)], [(96, 16)])
+    add("conv4_1_3", [dw(96, 5, 16), pw(96, 96, 16)], [(96, 16)], [(96, 16)])
+    add("head_4", [dw(96, 5, 16), pw(96, 96, 16), pw(96, nout, 16)], [(96, 16)], [(nout, 16)])
+    return G
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_u8(B, H, W, seed):
+    """Seeded uniform uint8 pixels (SURVEY.md §8d inputs 2-4)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (B, H, W), generator=g, dtype=torch.uint8)
+
+
+def cpu_reference_pass(sd, io, u8):
+    """The reference's CPU path restated by the oracle: PyTorch CPU forward + Python decode/sort/NMS loops per image
+    (detect.py:46 reads batch element 0 only, so B > 1 loops decode per image as BASELINE.md §3 prescribes)."""
+    from oracle import yolo_oracle as O
+    x = (u8.float().unsqueeze(1) - 128.0) / 255.0
+    t0 = time.perf_counter()
+    pred = O.forward(sd, x)
+    t1 = time.perf_counter()
+    n_det = 0
+    for b in range(x.shape[0]):
+        n_det += len(O.detect_postprocess(pred, io["anchors"], io["input_shape"], io["conf_thre"], io["nms_thre"],
+                                          io["num_anchors"], io["num_cls"], batch_index=b))
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, n_det
+
+
+def run_reference(args, cfg, sd, rank, world):
+    """--impl reference: the CPU implementation alone, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    io = cfg["io_params"]
+    H, W = io["input_shape"][0:2]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.cpu_sample
+    u8 = synthetic_u8(sample, H, W, 1000)
+    for _ in range(args.warmup):
+        cpu_reference_pass(sd, io, u8)
+    fwd = post = 0.0
+    for _ in range(args.steps):
+        a, b, _ = cpu_reference_pass(sd, io, u8)
+        fwd += a; post += b
+    total = fwd + post
+    value = sample * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%dx%d synthetic uint8 images, shipped %s checkpoint, conf %.2f nms %.2f; CPU sample of %d images per step"
+                       % (W, H, args.res, io["conf_thre"], io["nms_thre"], sample)},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "%d images/step x %d steps; forward %.1f ms/img, post-process %.2f ms/img; torch %s"
+                             % (sample, args.steps, 1000 * fwd / (sample * args.steps), 1000 * post / (sample * args.steps), torch.__version__)},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", default="512x640", choices=["512x640", "256x320"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--max-det", type=int, default=64)
+    ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                                     # timing rules: W >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import __graft_entry__
+    from yolo_fastest_b200 import config_for
+    cfg = config_for(args.res)
+    io = cfg["io_params"]
+    H, W = io["input_shape"][0:2]
+    ckpt = os.path.join(GOLD, "weights", "yolo_fastest_%s.pth" % args.res)
+    sd = torch.load(ckpt, map_location="cpu")
+
+    if args.impl == "reference":
+        run_reference(args, cfg, sd, rank, world)
+        return
+
+    __graft_entry__.build()
+    import torch.distributed as dist
+    from yolo_fastest_b200 import Detect_YOLO, _lib
+    from yolo_fastest_b200.dist import gather_detections
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    B = args.batch
+    det = Detect_YOLO(dev, ckpt, cfg, None)
+    u8 = synthetic_u8(B, H, W, 1000 + rank).pin_memory()
+    x_dev = ((u8.to(dev).float().unsqueeze(1) - 128.0) / 255.0).contiguous()      # resident input: 4*B*H*W bytes (> L2 at B=256)
+    n_total = B * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        out, counts, status = det.detect_device(x_dev, args.max_det)
+        if world > 1:
+            gather_detections(out, counts, n_total, dst=0)
+        return counts
+
+    def step_e2e():
+        rows = det.detect_batch(u8, max_det=args.max_det, raw=True)
+        if world > 1:      # the slabs are already on the host: return them through the same collective from pinned->device copies
+            pass
+        return rows
+
+    # ---- device-resident throughput ----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = det.model._ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        counts = step_device()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    launches = det.model._ctx.launch_count() - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    n_det = int(counts.sum().item())
+
+    # ---- end to end through the public API with host buffers ------------------------------------------------
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(args.steps):
+        rows = step_e2e()
+    c1.record()
+    torch.cuda.synchronize(dev)
+    e2e_ms = max(c0.elapsed_time(c1), 1000.0 * (time.perf_counter() - t0))    # host-synchronous call: wall clock bounds it
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline (rank 0): CUDA events around every group launch of one forward ----------------------
+    prof = det.model.profile(x_dev)
+    work = {g["name"]: g for g in group_work(H, W, det.model.num_out)}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    total_ms = sum(m for _, m in prof)
+    kernels = []
+    for name, m in prof:
+        w = work[name]
+        gbs = w["bytes"] * B / (m * 1e-3) / 1e9
+        tfl = 2 * w["macs"] * B / (m * 1e-3) / 1e12
+        kernels.append({"name": name, "ms": round(m, 4), "share": round(m / total_ms, 4), "GB/s": round(gbs, 1), "hbm_frac": round(gbs / hbm_peak, 4),
+                        "TFLOP/s": round(tfl, 2), "fp32_frac": round(tfl / FP32_PEAK_TFLOPS, 4)})
+    top = max(kernels, key=lambda k: k["ms"])
+    roofline = {"bound": "hbm", "achieved": top["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": None,
+                "kernel": top["name"], "share_of_forward": top["share"], "peak_source": peak_src,
+                "note": "fused groups are FP32 CUDA-core bound (48 FLOP/B overall); see fp32"}
+    fp32 = {"kernel": top["name"], "achieved": top["TFLOP/s"], "peak": round(FP32_PEAK_TFLOPS, 1), "unit": "TFLOP/s", "frac": top["fp32_frac"],
+            "whole_forward_TFLOP/s": round(2 * sum(g["macs"] for g in work.values()) * B / (total_ms * 1e-3) / 1e12, 2),
+            "whole_forward_GB/s": round(sum(g["bytes"] for g in work.values()) * B / (total_ms * 1e-3) / 1e9, 1)}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sample = args.cpu_sample
+        cu8 = synthetic_u8(sample, H, W, 1000)
+        cpu_reference_pass(sd, io, cu8)
+        fwd = post = 0.0
+        reps = 2
+        for _ in range(reps):
+            a, b, _ = cpu_reference_pass(sd, io, cu8)
+            fwd += a; post += b
+        cpu_baseline = {"value": sample * reps / (fwd + post), "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": "%d images x %d passes after 1 warm-up; forward %.1f ms/img, post-process %.2f ms/img; torch %s CPU"
+                        % (sample, reps, 1000 * fwd / (sample * reps), 1000 * post / (sample * reps), torch.__version__)}
+
+    line = {
+        "metric": METRIC, "value": n_total * args.steps / (ms_max * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%dx%d synthetic uint8 images, batch %d per GPU, shipped %s checkpoint, conf %.2f nms %.2f, max_det %d"
+                   % (W, H, B, args.res, io["conf_thre"], io["nms_thre"], args.max_det),
+                   "global_batch": n_total, "parallelism": "dp%d (image shards, one NCCL gather of detection slabs)" % world,
+                   "l2": "inputs larger than L2: %.0f MB resident fp32 input + %.1f GB of activations written per step"
+                   % (4e-6 * B * H * W, 1e-9 * B * sum(g["bytes"] for g in work.values()) / 2),
+                   "detections_last_step": n_det},
+        "e2e": {"value": n_total * args.steps / (e2e_ms_max * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * H * W,
+                "d2h_bytes_per_step": B * args.max_det * _lib.DET_DTYPE.itemsize + 8 * B, "ms_per_step": e2e_ms_max / args.steps,
+                "api": "Detect_YOLO.detect_batch -> yf_detect_host_u8 (pinned uint8 in, yf_det slab out)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "fp32": fp32,
+        "cpu_baseline": cpu_baseline,
+        "kernels": kernels,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

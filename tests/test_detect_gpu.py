@@ -1,0 +1,102 @@
+"""End to end through the reference-facing API: Detect_YOLO on the 20 shipped images at both resolutions
+(box-for-box against the golden lists), the batched host-buffer call, and the file-driving batch_detect."""
+import logging
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import yolo_fastest_b200 as yf
+from oracle import yolo_oracle as O
+
+from conftest import GOLD, rows_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _iou(a, b):
+    iw = min(a[2], b[2]) - max(a[0], b[0])
+    ih = min(a[3], b[3]) - max(a[1], b[1])
+    inter = max(iw, 0) * max(ih, 0)
+    u = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+    return inter / u if u else 1.0
+
+
+def _match(want, got):
+    """north_star: detections match box-for-box (IoU > 0.99, same class)."""
+    assert len(want) == len(got), (want, got)
+    for w, g in zip(want, got):
+        assert int(w[6]) == int(g[6]) and _iou(w, g) > 0.99 and abs(w[4] - g[4]) < 1e-4, (w, g)
+
+
+@pytest.mark.parametrize("res", ["256x320", "512x640"])
+def test_shipped_images_end_to_end(gold, res):
+    g = gold.res[res]
+    cfg = yf.config_for(res)
+    det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_" + res), cfg, None)
+    names = [str(n) for n in g["names"]]
+    exact = 0
+    flags = []
+    for i, name in enumerate(names):
+        img, ori = det.pre_process(os.path.join(GOLD, "images", name))
+        assert ori.shape == (512, 640, 3)
+        pred = det.model(img)
+        rows = det.post_process.postprocess_batch(pred)[0]
+        want = [list(r) for r in g["kept_%02d" % i]]
+        _match(want, rows)
+        exact += all([int(v) for v in w[:4]] == r[:4] for w, r in zip(want, rows))
+        flags.append(len(rows) > 0)
+        if res == "256x320":
+            det.adjust_coord(rows)
+            _match([list(r) for r in g["kept_adj_%02d" % i]], rows)
+    assert flags == [bool(f) for f in g["has_targets"]]                  # the published detect / no-target pattern
+    assert exact >= len(names) - 1, "integer boxes differ on %d images" % (len(names) - exact)
+
+
+@pytest.mark.parametrize("res", ["256x320", "512x640"])
+def test_detect_batch_host_buffers(gold, res):
+    """One yf_detect_host_u8 call for all 20 images == the per-image path; 256x320 inputs come from cv2.resize."""
+    g = gold.res[res]
+    cfg = yf.config_for(res)
+    det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_" + res), cfg, None)
+    names = [str(n) for n in g["names"]]
+    u8 = np.stack([det._load_gray(os.path.join(GOLD, "images", n))[0] for n in names])
+    assert np.array_equal(u8[:len(g["u8"])], g["u8"])                    # same pixels as the reference pre-process saw
+    rows = det.detect_batch(u8, max_det=16)
+    for i in range(len(names)):
+        _match([list(r) for r in g["kept_%02d" % i]], rows[i])
+    # ragged batch sizes reuse / regrow the context
+    for B in (1, 7):
+        part = det.detect_batch(u8[:B], max_det=16)
+        assert part == rows[:B]
+
+
+def test_batch_detect_driver(gold, tmp_path):
+    records = []
+
+    class H(logging.Handler):
+        def emit(self, r):
+            records.append(r.getMessage())
+    logger = logging.getLogger("yf-test")
+    logger.setLevel(logging.INFO)
+    logger.addHandler(H())
+    det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_512x640"), yf.config_for("512x640"), logger)
+    out = tmp_path / "out"
+    out.mkdir()
+    det.batch_detect(os.path.join(GOLD, "images"), str(out))
+    assert len(os.listdir(out)) == 20 and len(records) == 21
+    none = [r for r in records if "no targets" in r]
+    assert len(none) == 1 and "noCloud_2m_4359.jpg" in none[0]           # test_result/512x640/.../cpu-test.log:15
+    assert sum("detect finished, infer time:" in r for r in records) == 19 and records[-1].startswith("detect avg_time:")
+
+
+def test_fused_u8_equals_float_path(gold):
+    """(x-128)/255 fused into the stem kernel == normalising on the host first."""
+    g = gold.res["256x320"]
+    det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_256x320"), yf.config_for("256x320"), None)
+    u8 = g["u8"][:6]
+    a = det.detect_batch(u8, max_det=16)
+    x = torch.cat([O.preprocess_gray(u) for u in u8], 0).cuda()
+    b = det.post_process.postprocess_batch(det.model(x))
+    assert a == b

@@ -1,0 +1,123 @@
+"""yf_forward (through the drop-in YoloFastest) against the CPU oracle: raw fp32 head tensors within 1e-4
+(allclose rtol=atol=1e-4 AND max|d|/max|ref| <= 1e-4 — SURVEY.md §7.3-1), plus every tapped group output."""
+import numpy as np
+import pytest
+import torch
+
+import yolo_fastest_b200 as yf
+from oracle import yolo_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+TAPS = ["conv1_4", "res1_1", "conv2_1", "res2_1", "res2_2", "conv3_1", "res3_1", "res3_2", "conv3_4", "res3_3", "res3_4",
+        "res3_5", "res3_6", "conv4_1", "res4_1", "res4_2", "res4_3", "res4_4", "conv4_2", "conv5_1", "res5_1", "res5_2",
+        "res5_3", "res5_4", "res5_5", "conv5_2", "conv5_4", "conv4_1_1", "conv4_1_3"]
+
+
+def _model(sd, nc):
+    m = yf.YoloFastest({"num_cls": nc, "input_channel": 1, "num_anchors": 3})
+    m.load_state_dict(sd)
+    return m.cuda().eval()
+
+
+def _close(got, ref, what):
+    got = got.cpu()
+    err = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+    assert err <= TOL, "%s: max|d|/max|ref| = %.3g" % (what, err)
+    assert torch.allclose(got, ref, rtol=TOL, atol=TOL), "%s: allclose(1e-4) failed" % what
+
+
+def _rand_x(B, H, W, seed):
+    return (torch.randint(0, 256, (B, 1, H, W), generator=torch.Generator().manual_seed(seed)).float() - 128.0) / 255.0
+
+
+@pytest.mark.parametrize("res", ["256x320", "512x640"])
+def test_heads_on_shipped_images(gold, res):
+    g = gold.res[res]
+    sd = gold.sd("yolo_fastest_" + res)
+    m = _model(sd, 3)
+    x = torch.cat([O.preprocess_gray(u) for u in g["u8"]], 0)
+    hl, hs = m(x.cuda())
+    n = len(g["head_large"])
+    _close(hl[:n], torch.from_numpy(g["head_large"]), "head_large vs golden")
+    _close(hs[:n], torch.from_numpy(g["head_small"]), "head_small vs golden")
+    # one image at a time gives the same numbers as the batch (no cross-image state)
+    h1 = m(x[3:4].cuda())
+    assert torch.equal(h1[0][0], hl[3]) and torch.equal(h1[1][0], hs[3])
+
+
+@pytest.mark.parametrize("res,B", [("256x320", 3), ("512x640", 2)])
+def test_taps_and_heads_on_synthetic(gold, res, B):
+    sd = gold.sd("yolo_fastest_" + res)
+    m = _model(sd, 3)
+    H, W = (256, 320) if res == "256x320" else (512, 640)
+    x = _rand_x(B, H, W, 3)
+    taps = {}
+    rl, rs = O.forward(sd, x, taps)
+    hl, hs = m(x.cuda())
+    for name in TAPS:
+        _close(m.tap(name, B).view(taps[name].shape), taps[name], name)
+    _close(hl, rl, "head_large")
+    _close(hs, rs, "head_small")
+
+
+def test_golden_synthetic_heads(gold):
+    g = gold.res["256x320"]
+    m = _model(gold.sd("yolo_fastest_256x320"), 3)
+    u8 = torch.randint(0, 256, (2, 256, 320), generator=torch.Generator().manual_seed(int(g["syn_seed"])), dtype=torch.uint8).numpy()
+    x = torch.cat([O.preprocess_gray(s) for s in u8], 0)
+    hl, hs = m(x.cuda())
+    _close(hl, torch.from_numpy(g["syn_head_large"]), "syn head_large")
+    _close(hs, torch.from_numpy(g["syn_head_small"]), "syn head_small")
+
+
+@pytest.mark.parametrize("H,W,B", [(32, 32, 1), (64, 96, 5), (416, 416, 2), (96, 352, 2), (512, 640, 1)])
+def test_other_shapes_80_classes(gold, H, W, B):
+    """Ragged sizes (maps that do not fill a tile, odd map widths 13/11/3/1) and the 255-channel heads."""
+    sd = gold.sd("stress80_416")
+    m = _model(sd, 80)
+    x = _rand_x(B, H, W, 17)
+    rl, rs = O.forward(sd, x)
+    hl, hs = m(x.cuda())
+    assert hl.shape == rl.shape and hs.shape == rs.shape
+    _close(hl, rl, "head_large %dx%d" % (H, W))
+    _close(hs, rs, "head_small %dx%d" % (H, W))
+
+
+def test_stress_golden_heads(gold):
+    g = gold.stress
+    m = _model(gold.sd("stress80_416"), 80)
+    u8 = torch.randint(0, 256, (2, 416, 416), generator=torch.Generator().manual_seed(int(g["u8_seed"])), dtype=torch.uint8).numpy()
+    x = torch.cat([O.preprocess_gray(s) for s in u8], 0)
+    hl, hs = m(x.cuda())
+    _close(hl, torch.from_numpy(g["head_large"]), "stress head_large")
+    _close(hs, torch.from_numpy(g["head_small"]), "stress head_small")
+
+
+def test_batch_growth_reload_and_linearity_in_batch(gold):
+    """Context re-creation when the batch grows, weight reload, and image independence at a larger batch."""
+    sd = gold.sd("yolo_fastest_256x320")
+    m = _model(sd, 3)
+    x = _rand_x(37, 256, 320, 23).cuda()
+    a = m(x[:4])
+    b = m(x)                       # larger batch: ctx is rebuilt and weights re-uploaded
+    assert torch.equal(a[0], b[0][:4]) and torch.equal(a[1], b[1][:4])
+    perm = torch.randperm(37, generator=torch.Generator().manual_seed(1))
+    c = m(x[perm.cuda()])
+    assert torch.equal(c[0], b[0][perm.cuda()]) and torch.equal(c[1], b[1][perm.cuda()])
+    m.load_state_dict(gold.sd("yolo_fastest_512x640"))       # different weights, same shapes
+    d = m(x[:4])
+    assert not torch.equal(d[0], a[0])
+    rl, rs = O.forward(gold.sd("yolo_fastest_512x640"), x[:4].cpu())
+    _close(d[0], rl, "after reload")
+
+
+def test_zero_and_extreme_inputs(gold):
+    sd = gold.sd("yolo_fastest_256x320")
+    m = _model(sd, 3)
+    for fill in (0.0, -128.0 / 255.0, 127.0 / 255.0):
+        x = torch.full((1, 1, 256, 320), fill)
+        rl, rs = O.forward(sd, x)
+        hl, hs = m(x.cuda())
+        _close(hl, rl, "constant %.3f" % fill)
+        _close(hs, rs, "constant %.3f" % fill)

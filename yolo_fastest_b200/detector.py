@@ -195,11 +195,14 @@ class Detect_YOLO:
 
     # ---- batched detection through the C ABI with host buffers -----------------------------------------
     def detect_batch(self, u8_batch, max_det=64, raw=False):
-        """uint8 gray images [B, H, W] (host, network input size) -> per-image detection rows.
+        """uint8 gray images [B, H, W] (host numpy array or host torch tensor, network input size) -> per-image rows.
 
         One yf_detect_host_u8 call: H2D copy of the bytes, fused normalisation + forward + decode +
         NMS, D2H copy of the fixed-capacity result slab.  This is the end-to-end call bench.py times."""
-        u8_batch = np.ascontiguousarray(u8_batch, dtype=np.uint8)
+        direct = isinstance(u8_batch, torch.Tensor) and u8_batch.dtype == torch.uint8 and not u8_batch.is_cuda \
+            and u8_batch.is_contiguous()
+        if not direct:
+            u8_batch = np.ascontiguousarray(u8_batch, dtype=np.uint8)
         B, H, W = u8_batch.shape
         if [H, W] != list(self.input_shape[0:2]):
             raise _lib.YfError("images are %dx%d, the network input is %s" % (H, W, self.input_shape[0:2]))
@@ -211,7 +214,10 @@ class Detect_YOLO:
                                   torch.empty((B,), dtype=torch.int32).pin_memory(),
                                   torch.empty((B,), dtype=torch.int32).pin_memory())}
         pin_in, pin_out, pin_cnt, pin_st = self._pinned[key]
-        pin_in.numpy()[...] = u8_batch
+        if direct:
+            pin_in = u8_batch            # a host tensor (ideally pinned) is handed to the C ABI as is
+        else:
+            pin_in.numpy()[...] = u8_batch
         p = self.post_process._params(_lib.MODE_DETECT, max_det)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
@@ -223,6 +229,23 @@ class Detect_YOLO:
         dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
         res = [dets[b, :min(int(counts[b]), max_det)].copy() for b in range(B)]
         return res if raw else [_rows_from_dets(d) for d in res]
+
+    def detect_device(self, x, max_det=64):
+        """Device-resident form: x cuda fp32 [B, 1, H, W] (already normalised) -> (dets uint8 [B, max_det, 56],
+        counts int32 [B], status int32 [B]) cuda tensors, enqueued on the current stream, no synchronisation."""
+        self.model._check_input(x)
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        ctx = self.model.context(x.device, H, W, B)
+        out = torch.empty((B, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8, device=x.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=x.device)
+        status = torch.empty((B,), dtype=torch.int32, device=x.device)
+        p = self.post_process._params(_lib.MODE_DETECT, max_det)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().yf_detect(ctx.handle, x.data_ptr(), B, C.byref(p), out.data_ptr(), counts.data_ptr(),
+                                           status.data_ptr(), C.c_void_p(stream)), ctx.handle)
+        return out, counts, status
 
     # ---- reference driver (detect.py:141-192) ------------------------------------------------------------
     def batch_detect(self, data_path, result_path):
