@@ -161,24 +161,79 @@ struct yf_ctx {
 // group configurations (tile shapes tuned for the 640x512 / 320x256 maps; any H, W multiple of 32 works)
 //        IrbCfg<CIN, CMID, COUT, KS, S, TH, TW, MC, PN1, PN3, RH, NT, MINB, EXPAND, RES, RELU_OUT, DUAL, HEAD>
 // ---------------------------------------------------------------------------------------------
-using CfgStem = StemCfg<8, 40, 128, 4>;
-using CfgRes1 = IrbCfg<4, 8, 4, 3, 1, 8, 40, 8, 8, 4, 8, 128, 4, true, true, false, false>;
-using CfgDense = DenseCfg<4, 40, 8, 128, 3>;
-using CfgRes2 = IrbCfg<8, 32, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 3, true, true, false, false>;
-using CfgDown2 = IrbCfg<8, 32, 8, 3, 2, 4, 40, 16, 8, 4, 4, 128, 2, true, false, false, false>;
-using CfgRes3a = IrbCfg<8, 48, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 3, true, true, false, false>;
-using CfgWide3 = IrbCfg<8, 48, 16, 3, 1, 8, 40, 16, 8, 8, 8, 128, 3, true, false, false, false>;
-using CfgRes3b = IrbCfg<16, 96, 16, 3, 1, 8, 40, 16, 8, 8, 8, 256, 2, true, true, false, false>;
-using CfgDown3 = IrbCfg<16, 96, 24, 3, 2, 4, 40, 8, 8, 8, 4, 128, 2, true, false, false, false>;
-using CfgRes4 = IrbCfg<24, 136, 24, 3, 1, 8, 40, 16, 8, 8, 8, 256, 2, true, true, false, false>;
-using CfgDown4 = IrbCfg<24, 136, 48, 3, 2, 4, 20, 16, 8, 8, 4, 128, 2, true, false, true, true>;
-using CfgRes5 = IrbCfg<48, 224, 48, 3, 1, 8, 20, 16, 8, 8, 8, 128, 2, true, true, false, false>;
-using CfgPw52 = PwCfg<48, 96, 80, 8, 256, true>;
-using CfgNeckS1 = IrbCfg<96, 96, 128, 5, 1, 8, 20, 32, 4, 8, 4, 320, 1, false, false, false, false>;
-using CfgNeckS2 = IrbCfg<128, 128, 128, 5, 1, 8, 20, 32, 4, 8, 4, 320, 1, false, false, false, false, 1>;
-using CfgUpCat = UpCatCfg<8, 20, 16, 256, 2>;
-using CfgNeckL1 = IrbCfg<96, 96, 96, 5, 1, 8, 20, 32, 4, 8, 4, 256, 2, false, false, false, false>;
-using CfgNeckL2 = IrbCfg<96, 96, 96, 5, 1, 8, 20, 32, 4, 8, 4, 256, 2, false, false, false, false, 1>;
+// every configuration can be overridden with -DYF_CFG...="..." (tools/tune.py builds variants that way)
+#ifndef YF_CFGSTEM
+#define YF_CFGSTEM StemCfg<8, 40, 128, 4>
+#endif
+using CfgStem = YF_CFGSTEM;
+#ifndef YF_CFGRES1
+#define YF_CFGRES1 IrbCfg<4, 8, 4, 3, 1, 8, 40, 8, 8, 4, 8, 128, 4, true, true, false, false>
+#endif
+using CfgRes1 = YF_CFGRES1;
+#ifndef YF_CFGDENSE
+#define YF_CFGDENSE DenseCfg<4, 40, 8, 128, 3>
+#endif
+using CfgDense = YF_CFGDENSE;
+#ifndef YF_CFGRES2
+#define YF_CFGRES2 IrbCfg<8, 32, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 3, true, true, false, false>
+#endif
+using CfgRes2 = YF_CFGRES2;
+#ifndef YF_CFGDOWN2
+#define YF_CFGDOWN2 IrbCfg<8, 32, 8, 3, 2, 4, 40, 16, 8, 4, 4, 128, 2, true, false, false, false>
+#endif
+using CfgDown2 = YF_CFGDOWN2;
+#ifndef YF_CFGRES3A
+#define YF_CFGRES3A IrbCfg<8, 48, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 3, true, true, false, false>
+#endif
+using CfgRes3a = YF_CFGRES3A;
+#ifndef YF_CFGWIDE3
+#define YF_CFGWIDE3 IrbCfg<8, 48, 16, 3, 1, 8, 40, 16, 8, 8, 8, 128, 3, true, false, false, false>
+#endif
+using CfgWide3 = YF_CFGWIDE3;
+#ifndef YF_CFGRES3B
+#define YF_CFGRES3B IrbCfg<16, 96, 16, 3, 1, 8, 40, 16, 8, 8, 8, 256, 2, true, true, false, false>
+#endif
+using CfgRes3b = YF_CFGRES3B;
+#ifndef YF_CFGDOWN3
+#define YF_CFGDOWN3 IrbCfg<16, 96, 24, 3, 2, 4, 40, 8, 8, 8, 4, 128, 2, true, false, false, false>
+#endif
+using CfgDown3 = YF_CFGDOWN3;
+#ifndef YF_CFGRES4
+#define YF_CFGRES4 IrbCfg<24, 136, 24, 3, 1, 8, 40, 16, 8, 8, 8, 256, 2, true, true, false, false>
+#endif
+using CfgRes4 = YF_CFGRES4;
+#ifndef YF_CFGDOWN4
+#define YF_CFGDOWN4 IrbCfg<24, 136, 48, 3, 2, 4, 20, 16, 8, 8, 4, 128, 2, true, false, true, true>
+#endif
+using CfgDown4 = YF_CFGDOWN4;
+#ifndef YF_CFGRES5
+#define YF_CFGRES5 IrbCfg<48, 224, 48, 3, 1, 8, 20, 16, 8, 8, 8, 128, 2, true, true, false, false>
+#endif
+using CfgRes5 = YF_CFGRES5;
+#ifndef YF_CFGPW52
+#define YF_CFGPW52 PwCfg<48, 96, 80, 8, 256, true>
+#endif
+using CfgPw52 = YF_CFGPW52;
+#ifndef YF_CFGNECKS1
+#define YF_CFGNECKS1 IrbCfg<96, 96, 128, 5, 1, 8, 20, 32, 4, 8, 4, 320, 1, false, false, false, false>
+#endif
+using CfgNeckS1 = YF_CFGNECKS1;
+#ifndef YF_CFGNECKS2
+#define YF_CFGNECKS2 IrbCfg<128, 128, 128, 5, 1, 8, 20, 32, 4, 8, 4, 320, 1, false, false, false, false, 1>
+#endif
+using CfgNeckS2 = YF_CFGNECKS2;
+#ifndef YF_CFGUPCAT
+#define YF_CFGUPCAT UpCatCfg<8, 20, 16, 256, 2>
+#endif
+using CfgUpCat = YF_CFGUPCAT;
+#ifndef YF_CFGNECKL1
+#define YF_CFGNECKL1 IrbCfg<96, 96, 96, 5, 1, 8, 20, 32, 4, 8, 4, 256, 2, false, false, false, false>
+#endif
+using CfgNeckL1 = YF_CFGNECKL1;
+#ifndef YF_CFGNECKL2
+#define YF_CFGNECKL2 IrbCfg<96, 96, 96, 5, 1, 8, 20, 32, 4, 8, 4, 256, 2, false, false, false, false, 1>
+#endif
+using CfgNeckL2 = YF_CFGNECKL2;
 
 namespace {
 
@@ -333,11 +388,11 @@ int64_t pack_upcat(std::vector<float>& out, const Folded& f) {
         o[C::OFF_B + n] = f.b("conv4_1_1")[n];
     }
     const float* wt = f.w("deconv5_1");   // [cin 96][cout 96][2][2]
-    for (int py = 0; py < 2; ++py)
-        for (int c = 0; c < 96; ++c)
-            for (int m = 0; m < 96; ++m)
-                for (int px = 0; px < 2; ++px)
-                    o[C::OFF_WT + ((py * 96 + c) * 96 + m) * 2 + px] = wt[((c * 96 + m) * 2 + py) * 2 + px];
+    for (int c = 0; c < 96; ++c)
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px)
+                for (int m = 0; m < 96; ++m)
+                    o[C::OFF_WT + ((c * 4) + py * 2 + px) * 96 + m] = wt[((c * 96 + m) * 2 + py) * 2 + px];
     for (int m = 0; m < 96; ++m) o[C::OFF_BT + m] = f.b("deconv5_1")[m];
     return off;
 }

@@ -33,7 +33,13 @@ struct Geo {
     static constexpr int IWS = rup(IW, 4);            // row stride in smem (float4 aligned)
     static constexpr int IPIX = IH * IWS;
     static constexpr int OPIX = TH * TW;
+    // Stride-2 stages keep their INPUT rows (E) de-interleaved by column parity: [even cols (EW) | odd cols (TW)].
+    // Four adjacent outputs then read three conflict-free 128-bit words per row instead of a stride-2 gather
+    // (which is a 2-way/8-way bank conflict with the lanes of a warp on consecutive output groups).
+    static constexpr bool SPLIT = (S == 2);
+    static constexpr int EW = SPLIT ? rup(TW + 1, 4) : 0;
     static_assert(TW % 4 == 0, "tile width must be a multiple of 4");
+    static_assert(!SPLIT || (KS == 3 && EW + TW == IWS), "parity split is laid out for 3x3 stride 2");
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -93,46 +99,49 @@ __device__ __forceinline__ void pw_halo(const float* __restrict__ Xs, const floa
             m[i] = rowok && (j0 + i < G::IW) && ((unsigned)(gx0 + i) < (unsigned)Win);
             any |= m[i];
         }
-        if (!any) {
-#pragma unroll
-            for (int n = 0; n < PN; ++n) st4(e + n * G::IPIX, make_float4(0.f, 0.f, 0.f, 0.f));
-            continue;
-        }
         float acc[PN][4];
-#pragma unroll
-        for (int n4 = 0; n4 < PN / 4; ++n4) {
-            const float4 b = ld4(bias + cg * PN + n4 * 4);
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[n4 * 4 + q][i] = bb[q];
-        }
-        const float* xp = Xs + p0;
-        const float* wp = W + cg * PN;
-#pragma unroll 8
-        for (int k = 0; k < K; ++k) {
-            const float4 xv = ld4(xp + k * G::IPIX);
-            const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (any) {
 #pragma unroll
             for (int n4 = 0; n4 < PN / 4; ++n4) {
-                const float4 w = ld4(wp + k * MC + n4 * 4);
-                const float w4[4] = {w.x, w.y, w.z, w.w};
+                const float4 b = ld4(bias + cg * PN + n4 * 4);
+                const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[n4 * 4 + q][i] = fmaf(w4[q], x4[i], acc[n4 * 4 + q][i]);
+                    for (int i = 0; i < 4; ++i) acc[n4 * 4 + q][i] = bb[q];
+            }
+            const float* xp = Xs + p0;
+            const float* wp = W + cg * PN;
+#pragma unroll 8
+            for (int k = 0; k < K; ++k) {
+                const float4 xv = ld4(xp + k * G::IPIX);
+                const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int n4 = 0; n4 < PN / 4; ++n4) {
+                    const float4 w = ld4(wp + k * MC + n4 * 4);
+                    const float w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[n4 * 4 + q][i] = fmaf(w4[q], x4[i], acc[n4 * 4 + q][i]);
+                }
             }
         }
 #pragma unroll
         for (int n = 0; n < PN; ++n) {
             float4 o;
-            o.x = m[0] ? fmaxf(acc[n][0], 0.f) : 0.f;
-            o.y = m[1] ? fmaxf(acc[n][1], 0.f) : 0.f;
-            o.z = m[2] ? fmaxf(acc[n][2], 0.f) : 0.f;
-            o.w = m[3] ? fmaxf(acc[n][3], 0.f) : 0.f;
-            st4(e + n * G::IPIX, o);
-            if (DUAL) {
+            o.x = (any && m[0]) ? fmaxf(acc[n][0], 0.f) : 0.f;
+            o.y = (any && m[1]) ? fmaxf(acc[n][1], 0.f) : 0.f;
+            o.z = (any && m[2]) ? fmaxf(acc[n][2], 0.f) : 0.f;
+            o.w = (any && m[3]) ? fmaxf(acc[n][3], 0.f) : 0.f;
+            if (G::SPLIT) {
+                float* er = Es + (cg * PN + n) * G::IPIX + r * G::IWS + (j0 >> 1);
+                *reinterpret_cast<float2*>(er) = make_float2(o.x, o.z);                                  // columns j0, j0+2
+                if ((j0 >> 1) < G::TW) *reinterpret_cast<float2*>(er + G::EW) = make_float2(o.y, o.w);   // columns j0+1, j0+3
+            } else {
+                st4(e + n * G::IPIX, o);
+            }
+            if (DUAL && any) {
                 // pixels this tile owns (not halo): rows/cols [P, P + T*S)
                 const bool rown = r >= G::P && r < G::P + G::TH * G::S;
                 if (rown && (cg * PN + n) < skip_valid) {
@@ -163,6 +172,21 @@ __device__ __forceinline__ void load_row(float (&dst)[NV], const float* __restri
     if (NV % 2 == 1) dst[NV - 1] = p[NV - 1];
 }
 
+// The NV = 3*S + KS input columns feeding 4 adjacent outputs (output group g) of one input row.
+// S == 1: contiguous. S == 2 (parity-split row, EW even columns then the odd ones): v[2i+dx] for i<4, dx<3.
+template <class G>
+__device__ __forceinline__ void load_window(float (&dst)[3 * G::S + G::KS], const float* __restrict__ row, int g) {
+    if (G::SPLIT) {
+        const float4 a = ld4(row + 4 * g);
+        const float4 b = ld4(row + 4 * g + 4);
+        const float4 c = ld4(row + G::EW + 4 * g);
+        dst[0] = a.x; dst[2] = a.y; dst[4] = a.z; dst[6] = a.w; dst[8] = b.x;
+        dst[1] = c.x; dst[3] = c.y; dst[5] = c.z; dst[7] = c.w;
+    } else {
+        load_row<3 * G::S + G::KS>(dst, row + 4 * g * G::S);
+    }
+}
+
 // Stage 2: depthwise KSxKS stride S + bias + ReLU:  D[m][oy][ox] = relu(sum W[m][dy][dx] E[m][oy*S+dy][ox*S+dx] + b[m]).
 // Thread item = one channel x a strip of 4 output columns x RH output rows; the KS input rows of
 // the window live in registers and slide down (S new row loads per output row).
@@ -184,11 +208,11 @@ __device__ __forceinline__ void dw_stage(const float* __restrict__ Es, const flo
 #pragma unroll
         for (int t = 0; t < KS * KS; ++t) w[t] = Wd[m * KS * KS + t];
         const float b = bd[m];
-        const float* e = Es + m * G::IPIX + (seg * RH * S) * G::IWS + 4 * g * S;
+        const float* e = Es + m * G::IPIX + (seg * RH * S) * G::IWS;
         float* d = Ds + m * G::OPIX + (seg * RH) * G::TW + 4 * g;
         float win[KS][NV];
 #pragma unroll
-        for (int dd = 0; dd < KS - S; ++dd) load_row<NV>(win[dd + S], e + dd * G::IWS);
+        for (int dd = 0; dd < KS - S; ++dd) load_window<G>(win[dd + S], e + dd * G::IWS, g);
 #pragma unroll
         for (int oy = 0; oy < RH; ++oy) {
 #pragma unroll
@@ -196,7 +220,7 @@ __device__ __forceinline__ void dw_stage(const float* __restrict__ Es, const flo
 #pragma unroll
                 for (int v = 0; v < NV; ++v) win[dd][v] = win[dd + S][v];
 #pragma unroll
-            for (int dd = KS - S; dd < KS; ++dd) load_row<NV>(win[dd], e + (oy * S + dd) * G::IWS);
+            for (int dd = KS - S; dd < KS; ++dd) load_window<G>(win[dd], e + (oy * S + dd) * G::IWS, g);
             float a[4] = {b, b, b, b};
 #pragma unroll
             for (int dy = 0; dy < KS; ++dy)
@@ -438,8 +462,9 @@ struct StemCfg {
     static constexpr int NT = NT_, MINB = MINB_;
     using G = Geo<3, 1, TH_, TW_>;
     static constexpr int RH = 2 * G::IH + 1;          // raw input rows feeding the conv0 halo tile
-    static constexpr int RW = 2 * G::IWS + 1;
-    static constexpr int RWS = rup(RW, 4);
+    static constexpr int RW = 2 * G::IWS + 1;         // raw input columns
+    static constexpr int REW = G::IWS + 4;            // raw rows are stored parity-split: [even cols (REW) | odd cols (IWS)]
+    static constexpr int RWS = REW + G::IWS;
     static constexpr int OFF_W0 = 0, OFF_B0 = 72, OFF_W1 = 80, OFF_B1 = 144, OFF_WD = 152, OFF_BD = 224, OFF_W2 = 232, OFF_B2 = 264;
     static constexpr int WFLOATS = 268;
     static constexpr int RS = RH * RWS;
@@ -468,7 +493,8 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
     const int ry0 = 2 * iy0 - 1, rx0 = 2 * ix0 - 1;    // raw origin (conv0: stride 2, pad 1)
     // raw tile
     for (int idx = threadIdx.x; idx < C::RS; idx += NT) {
-        const int r = idx / C::RWS, j = idx - r * C::RWS;
+        const int r = idx / C::RWS, jj = idx - r * C::RWS;
+        const int j = jj < C::REW ? 2 * jj : 2 * (jj - C::REW) + 1;     // raw column held at split position jj
         const int gy = ry0 + r, gx = rx0 + j;
         float v = 0.f;
         if (j < C::RW && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win) {
@@ -494,9 +520,13 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
                 for (int i = 0; i < 4; ++i) a[c][i] = Ws[C::OFF_B0 + c];
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-                float v[9];
-                const float* rp = Rs + (2 * r + dy) * C::RWS + 2 * j0;
-                load_row<9>(v, rp);
+                float v[9];   // raw columns 2*j0 .. 2*j0+8 of this row: v[2i+dx] feeds output i, tap dx
+                const float* rp = Rs + (2 * r + dy) * C::RWS + j0;
+                {
+                    const float4 a = ld4(rp), b = ld4(rp + 4), c = ld4(rp + C::REW);
+                    v[0] = a.x; v[2] = a.y; v[4] = a.z; v[6] = a.w; v[8] = b.x;
+                    v[1] = c.x; v[3] = c.y; v[5] = c.z; v[7] = c.w;
+                }
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
                     const float4 wa = ld4(W0 + (dy * 3 + dx) * 8);
@@ -601,7 +631,7 @@ dense_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __
     for (int c = 0; c < C::NCHUNK; ++c) {
         const float* Wc = Ws + c * C::CB;
         __syncthreads();
-        pw_halo<G, 4, C::MC, 4, NT, false>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win, nullptr, 0);
+        pw_halo<G, 4, C::MC, (C::MC % 8 == 0 ? 8 : 4), NT, false>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win, nullptr, 0);
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < C::IPT9; ++it) {
@@ -611,14 +641,14 @@ dense_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __
                 const int pg = item - cg * C::NPG;
                 const int p0 = pg * 4;
                 const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
-                const float* ep = Es + (oy * 2) * G::IWS + ox * 2;
+                const float* ep = Es + (oy * 2) * G::IWS;
                 const float* wp = Wc + C::OFF_WC + cg * 24;
 #pragma unroll 2
                 for (int m = 0; m < C::MC; ++m) {
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         float v[9];
-                        load_row<9>(v, ep + m * G::IPIX + dy * G::IWS);
+                        load_window<G>(v, ep + m * G::IPIX + dy * G::IWS, ox >> 2);
                         const float* w = wp + (m * 3 + dy) * 72;
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
@@ -753,28 +783,30 @@ pw_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __res
 // ---------------------------------------------------------------------------------------------
 // Fused upsample + concat + 1x1: deconv5_1 (ConvTranspose2d k2 s2 96->96 + BN + ReLU, yolo_fastest.py:42-48,140,208)
 // -> cat((conv4_2[136], deconv5_1[96]), 1) (:209) -> conv4_1_1 (1x1 232->96 + ReLU, :142).
-// The upsampled tensor and the concatenation never exist in memory: for each K-chunk the CTA either
-// stages 136-side skip channels or computes the 96 up-channels for its tile from the parent
-// (H/32) pixels, and accumulates the 1x1 into register tiles.
-// Packed weights: [Wa: 136*96 ([k][n])][Wb: 96*96 ([k][n])][b: 96]
-//                 [Wt: 2(py) * 96(c) * 96(m) * 2(px)][bt: 96]
+// The upsampled tensor and the concatenation never exist in HBM:
+//   phase A  U[m][2y+py][2x+px] = relu(sum_c Wt[c][py][px][m] * P[c][y][x] + bt[m]) for the tile's parent
+//            pixels — a 1x1 GEMM over parent pixels with one weight set per output parity — kept in smem;
+//   phase B  out = relu(Wa . skip + Wb . U + b), K streamed in chunks: skip channels staged from HBM,
+//            up channels read straight from the smem U tile.
+// Packed weights: [Wa: 136*96 ([k][n])][Wb: 96*96 ([k][n])][b: 96][Wt: 96(c) * 4(py*2+px) * 96(m)][bt: 96]
 // ---------------------------------------------------------------------------------------------
 template <int TH_, int TW_, int KC_, int NT_, int MINB_>
 struct UpCatCfg {
     static constexpr int TH = TH_, TW = TW_, KC = KC_, NT = NT_, MINB = MINB_;
     static constexpr int CS = 136, CU = 96, N = 96;
     static constexpr int OPIX = TH * TW, PH = TH / 2, PW = TW / 2, PPIX = PH * PW;
-    static constexpr int OFF_WA = 0, OFF_WB = CS * N, OFF_B = OFF_WB + CU * N, OFF_WT = OFF_B + N, OFF_BT = OFF_WT + 2 * CU * CU * 2;
+    static constexpr int OFF_WA = 0, OFF_WB = CS * N, OFF_B = OFF_WB + CU * N, OFF_WT = OFF_B + N, OFF_BT = OFF_WT + CU * 4 * CU;
     static constexpr int WFLOATS = OFF_BT + CU;
     static constexpr int PN = 8;
-    static constexpr int IPT = cdiv((OPIX / 4) * (N / PN), NT);
+    static constexpr int IPT = cdiv((OPIX / 4) * (N / PN), NT);               // phase B items per thread
+    static constexpr int IPTA = cdiv((PPIX / 4) * 4 * (CU / PN), NT);         // phase A items per thread
     static constexpr int CSP = rup(CS, KC);
     static constexpr int PS = CU * PPIX;            // parent tile [96][PPIX]
-    static constexpr int BS = KC * OPIX;            // K-chunk buffer
-    static constexpr int WS = KC * N;               // conv4_1_1 rows of the chunk
-    static constexpr int SMEM_FLOATS = PS + BS + WS;
+    static constexpr int US = CU * OPIX;            // upsampled tile [96][OPIX]
+    static constexpr int SCR = cmax(KC * 4 * CU, KC * OPIX + KC * N);   // phase A weight chunk | phase B (skip chunk + weight rows)
+    static constexpr int SMEM_FLOATS = PS + US + SCR;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
-    static_assert(TH % 2 == 0 && TW % 4 == 0 && CU % KC == 0 && KC % 8 == 0, "bad upcat tiling");
+    static_assert(TH % 2 == 0 && TW % 4 == 0 && CU % KC == 0 && KC % 4 == 0 && PPIX % 4 == 0, "bad upcat tiling");
     static_assert(SMEM_BYTES <= 227 * 1024, "upcat tile too large");
 };
 
@@ -785,18 +817,79 @@ upcat_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __rest
     constexpr int NT = C::NT;
     extern __shared__ __align__(16) float smem[];
     float* Ps = smem;
-    float* Bs = Ps + C::PS;
-    float* Ws = Bs + C::BS;
+    float* Us = Ps + C::PS;
+    float* Sc = Us + C::US;
     const TileId t = tile_id(tiles_x, tiles_y);
     const int oy0 = t.ty * C::TH, ox0 = t.tx * C::TW;
     const int Hl = H / 2, Wl = W / 2;
-    // parent tile
     for (int idx = threadIdx.x; idx < C::PS; idx += NT) {
         const int c = idx / C::PPIX, p = idx - c * C::PPIX;
         const int py = p / C::PW, px = p - py * C::PW;
         const int gy = oy0 / 2 + py, gx = ox0 / 2 + px;
         Ps[idx] = (gy < Hl && gx < Wl) ? __ldg(low + (((size_t)t.b * C::CU + c) * Hl + gy) * Wl + gx) : 0.f;
     }
+    // ---- phase A: item = 4 consecutive parent pixels x one output parity x 8 up channels ----------------
+    {
+        constexpr int NPG = C::PPIX / 4, NCG = C::CU / C::PN;
+        float u[C::IPTA][C::PN][4];
+#pragma unroll
+        for (int it = 0; it < C::IPTA; ++it)
+#pragma unroll
+            for (int n = 0; n < C::PN; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) u[it][n][i] = 0.f;
+        for (int c0 = 0; c0 < C::CU; c0 += C::KC) {
+            __syncthreads();                                           // previous chunk consumed (first: Ps visible)
+            copy_f4<NT>(Sc, wts + C::OFF_WT + (size_t)c0 * 4 * C::CU, C::KC * 4 * C::CU);
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < C::IPTA; ++it) {
+                const int item = threadIdx.x + it * NT;
+                if (item < NPG * 4 * NCG) {
+                    const int pg = item % NPG;
+                    const int par = (item / NPG) & 3;
+                    const int cg = item / (NPG * 4);
+                    const float* pp = Ps + (size_t)c0 * C::PPIX + pg * 4;
+                    const float* wp = Sc + par * C::CU + cg * C::PN;
+#pragma unroll 4
+                    for (int k = 0; k < C::KC; ++k) {
+                        const float4 pv = ld4(pp + k * C::PPIX);
+                        const float p4[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                        for (int n4 = 0; n4 < C::PN / 4; ++n4) {
+                            const float4 w = ld4(wp + k * 4 * C::CU + n4 * 4);
+                            const float w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) u[it][n4 * 4 + q][i] = fmaf(w4[q], p4[i], u[it][n4 * 4 + q][i]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < C::IPTA; ++it) {
+            const int item = threadIdx.x + it * NT;
+            if (item < NPG * 4 * NCG) {
+                const int pg = item % NPG;
+                const int par = (item / NPG) & 3;
+                const int cg = item / (NPG * 4);
+#pragma unroll
+                for (int n = 0; n < C::PN; ++n) {
+                    const int mch = cg * C::PN + n;
+                    const float b = __ldg(wts + C::OFF_BT + mch);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int p = pg * 4 + i;
+                        const int py = p / C::PW, px = p - py * C::PW;
+                        Us[mch * C::OPIX + (2 * py + (par >> 1)) * C::TW + 2 * px + (par & 1)] = fmaxf(u[it][n][i] + b, 0.f);
+                    }
+                }
+            }
+        }
+    }
+    // ---- phase B: 1x1 over the concatenation, K in chunks ------------------------------------------------
     float acc[C::IPT][C::PN][4];
 #pragma unroll
     for (int it = 0; it < C::IPT; ++it)
@@ -804,14 +897,14 @@ upcat_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __rest
         for (int n = 0; n < C::PN; ++n)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
-
+    float* Bs = Sc;
+    float* Ws = Sc + C::KC * C::OPIX;
     constexpr int NCH_S = C::CSP / C::KC, NCH_U = C::CU / C::KC;
     for (int c = 0; c < NCH_S + NCH_U; ++c) {
-        __syncthreads();     // previous chunk fully consumed (and Ps visible)
+        __syncthreads();     // previous chunk fully consumed (first: phase A done, Us visible)
         if (c < NCH_S) {
-            // stage skip channels [c*KC, c*KC+KC) of the tile (zero beyond 136) + their conv4_1_1 rows
             const int k0 = c * C::KC;
-            for (int idx = threadIdx.x; idx < C::BS; idx += NT) {
+            for (int idx = threadIdx.x; idx < C::KC * C::OPIX; idx += NT) {
                 const int k = idx / C::OPIX, p = idx - k * C::OPIX;
                 const int oy = p / C::TW, ox = p - oy * C::TW;
                 const int gy = oy0 + oy, gx = ox0 + ox;
@@ -819,55 +912,18 @@ upcat_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __rest
                 if (k0 + k < C::CS && gy < H && gx < W) v = __ldg(skip + (((size_t)t.b * C::CS + k0 + k) * H + gy) * W + gx);
                 Bs[idx] = v;
             }
-            for (int idx = threadIdx.x; idx < C::WS; idx += NT) {
+            for (int idx = threadIdx.x; idx < C::KC * C::N; idx += NT) {
                 const int k = idx / C::N;
                 Ws[idx] = (k0 + k < C::CS) ? __ldg(wts + C::OFF_WA + (size_t)k0 * C::N + idx) : 0.f;
             }
+            __syncthreads();
+            pw_accum<C::OPIX, C::KC, C::N, C::PN, C::IPT, NT>(Bs, Ws, acc);
         } else {
-            // compute up channels [m0, m0+KC): U[m][q] = relu(sum_c Wt[py][c][m][px] * P[c][parent(q)] + bt[m])
             const int m0 = (c - NCH_S) * C::KC;
-            copy_f4<NT>(Ws, wts + C::OFF_WB + (size_t)m0 * C::N, C::WS);
-            constexpr int NPG = C::OPIX / 4, NCG = C::KC / 8;
-            for (int item = threadIdx.x; item < NPG * NCG; item += NT) {
-                const int cg = item / NPG;
-                const int pg = item - cg * NPG;
-                const int p0 = pg * 4;
-                const int oy = p0 / C::TW, ox = p0 - oy * C::TW;
-                const int py = oy & 1;
-                const float* pp = Ps + (oy >> 1) * C::PW + (ox >> 1);
-                const float* wt = wts + C::OFF_WT + ((size_t)py * C::CU * C::CU + (m0 + cg * 8)) * 2;
-                float u[8][4];
-#pragma unroll
-                for (int n = 0; n < 8; ++n) {
-                    const float b = __ldg(wts + C::OFF_BT + m0 + cg * 8 + n);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) u[n][i] = b;
-                }
-#pragma unroll 4
-                for (int k = 0; k < C::CU; ++k) {
-                    const float2 pv = *reinterpret_cast<const float2*>(pp + k * C::PPIX);
-                    const float* wk = wt + (size_t)k * C::CU * 2;
-#pragma unroll
-                    for (int n4 = 0; n4 < 4; ++n4) {
-                        const float4 w = __ldg(reinterpret_cast<const float4*>(wk + n4 * 4));   // (m, px0) (m, px1) (m+1, px0) (m+1, px1)
-                        u[n4 * 2 + 0][0] = fmaf(w.x, pv.x, u[n4 * 2 + 0][0]);
-                        u[n4 * 2 + 0][1] = fmaf(w.y, pv.x, u[n4 * 2 + 0][1]);
-                        u[n4 * 2 + 0][2] = fmaf(w.x, pv.y, u[n4 * 2 + 0][2]);
-                        u[n4 * 2 + 0][3] = fmaf(w.y, pv.y, u[n4 * 2 + 0][3]);
-                        u[n4 * 2 + 1][0] = fmaf(w.z, pv.x, u[n4 * 2 + 1][0]);
-                        u[n4 * 2 + 1][1] = fmaf(w.w, pv.x, u[n4 * 2 + 1][1]);
-                        u[n4 * 2 + 1][2] = fmaf(w.z, pv.y, u[n4 * 2 + 1][2]);
-                        u[n4 * 2 + 1][3] = fmaf(w.w, pv.y, u[n4 * 2 + 1][3]);
-                    }
-                }
-#pragma unroll
-                for (int n = 0; n < 8; ++n)
-                    st4(Bs + (cg * 8 + n) * C::OPIX + p0,
-                        make_float4(fmaxf(u[n][0], 0.f), fmaxf(u[n][1], 0.f), fmaxf(u[n][2], 0.f), fmaxf(u[n][3], 0.f)));
-            }
+            copy_f4<NT>(Ws, wts + C::OFF_WB + (size_t)m0 * C::N, C::KC * C::N);
+            __syncthreads();
+            pw_accum<C::OPIX, C::KC, C::N, C::PN, C::IPT, NT>(Us + (size_t)m0 * C::OPIX, Ws, acc);
         }
-        __syncthreads();
-        pw_accum<C::OPIX, C::KC, C::N, C::PN, C::IPT, NT>(Bs, Ws, acc);
     }
     constexpr int NPG = C::OPIX / 4;
 #pragma unroll
