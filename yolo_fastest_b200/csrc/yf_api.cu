@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -96,6 +97,7 @@ void set_err(std::string* dst, const char* fmt, ...) {
 // context
 // ---------------------------------------------------------------------------------------------
 struct GroupArgs {
+    int nsm = 148;               // SM count (persistent grids)
     const float* x = nullptr;    // input activation
     const float* x2 = nullptr;   // second input (upcat: low-res tensor)
     float* y = nullptr;          // output activation (or head)
@@ -163,11 +165,11 @@ struct yf_ctx {
 // ---------------------------------------------------------------------------------------------
 // every configuration can be overridden with -DYF_CFG...="..." (tools/tune.py builds variants that way)
 #ifndef YF_CFGSTEM
-#define YF_CFGSTEM StemCfg<8, 40, 128, 4>
+#define YF_CFGSTEM StemCfg<8, 40, 256, 3>
 #endif
 using CfgStem = YF_CFGSTEM;
 #ifndef YF_CFGRES1
-#define YF_CFGRES1 IrbCfg<4, 8, 4, 3, 1, 8, 40, 8, 8, 4, 8, 128, 4, true, true, false, false>
+#define YF_CFGRES1 IrbCfg<4, 8, 4, 3, 1, 8, 40, 8, 4, 4, 8, 256, 3, true, true, false, false>
 #endif
 using CfgRes1 = YF_CFGRES1;
 #ifndef YF_CFGDENSE
@@ -175,19 +177,19 @@ using CfgRes1 = YF_CFGRES1;
 #endif
 using CfgDense = YF_CFGDENSE;
 #ifndef YF_CFGRES2
-#define YF_CFGRES2 IrbCfg<8, 32, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 3, true, true, false, false>
+#define YF_CFGRES2 IrbCfg<8, 32, 8, 3, 1, 16, 40, 8, 8, 4, 8, 256, 3, true, true, false, false>
 #endif
 using CfgRes2 = YF_CFGRES2;
 #ifndef YF_CFGDOWN2
-#define YF_CFGDOWN2 IrbCfg<8, 32, 8, 3, 2, 4, 40, 16, 8, 4, 4, 128, 2, true, false, false, false>
+#define YF_CFGDOWN2 IrbCfg<8, 32, 8, 3, 2, 4, 40, 8, 8, 4, 4, 128, 3, true, false, false, false>
 #endif
 using CfgDown2 = YF_CFGDOWN2;
 #ifndef YF_CFGRES3A
-#define YF_CFGRES3A IrbCfg<8, 48, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 3, true, true, false, false>
+#define YF_CFGRES3A IrbCfg<8, 48, 8, 3, 1, 8, 40, 8, 8, 4, 8, 128, 5, true, true, false, false>
 #endif
 using CfgRes3a = YF_CFGRES3A;
 #ifndef YF_CFGWIDE3
-#define YF_CFGWIDE3 IrbCfg<8, 48, 16, 3, 1, 8, 40, 16, 8, 8, 8, 128, 3, true, false, false, false>
+#define YF_CFGWIDE3 IrbCfg<8, 48, 16, 3, 1, 8, 40, 8, 8, 8, 8, 128, 4, true, false, false, false>
 #endif
 using CfgWide3 = YF_CFGWIDE3;
 #ifndef YF_CFGRES3B
@@ -195,7 +197,7 @@ using CfgWide3 = YF_CFGWIDE3;
 #endif
 using CfgRes3b = YF_CFGRES3B;
 #ifndef YF_CFGDOWN3
-#define YF_CFGDOWN3 IrbCfg<16, 96, 24, 3, 2, 4, 40, 8, 8, 8, 4, 128, 2, true, false, false, false>
+#define YF_CFGDOWN3 IrbCfg<16, 96, 24, 3, 2, 4, 40, 8, 8, 8, 4, 256, 2, true, false, false, false>
 #endif
 using CfgDown3 = YF_CFGDOWN3;
 #ifndef YF_CFGRES4
@@ -203,11 +205,11 @@ using CfgDown3 = YF_CFGDOWN3;
 #endif
 using CfgRes4 = YF_CFGRES4;
 #ifndef YF_CFGDOWN4
-#define YF_CFGDOWN4 IrbCfg<24, 136, 48, 3, 2, 4, 20, 16, 8, 8, 4, 128, 2, true, false, true, true>
+#define YF_CFGDOWN4 IrbCfg<24, 136, 48, 3, 2, 4, 20, 16, 8, 8, 4, 256, 2, true, false, true, true>
 #endif
 using CfgDown4 = YF_CFGDOWN4;
 #ifndef YF_CFGRES5
-#define YF_CFGRES5 IrbCfg<48, 224, 48, 3, 1, 8, 20, 16, 8, 8, 8, 128, 2, true, true, false, false>
+#define YF_CFGRES5 IrbCfg<48, 224, 48, 3, 1, 8, 20, 16, 8, 8, 8, 256, 2, true, true, false, false>
 #endif
 using CfgRes5 = YF_CFGRES5;
 #ifndef YF_CFGPW52
@@ -215,11 +217,11 @@ using CfgRes5 = YF_CFGRES5;
 #endif
 using CfgPw52 = YF_CFGPW52;
 #ifndef YF_CFGNECKS1
-#define YF_CFGNECKS1 IrbCfg<96, 96, 128, 5, 1, 8, 20, 32, 4, 8, 4, 320, 1, false, false, false, false>
+#define YF_CFGNECKS1 IrbCfg<96, 96, 128, 5, 1, 8, 20, 32, 4, 8, 4, 640, 1, false, false, false, false>
 #endif
 using CfgNeckS1 = YF_CFGNECKS1;
 #ifndef YF_CFGNECKS2
-#define YF_CFGNECKS2 IrbCfg<128, 128, 128, 5, 1, 8, 20, 32, 4, 8, 4, 320, 1, false, false, false, false, 1>
+#define YF_CFGNECKS2 IrbCfg<128, 128, 128, 5, 1, 8, 20, 32, 4, 8, 4, 640, 1, false, false, false, false, 1>
 #endif
 using CfgNeckS2 = YF_CFGNECKS2;
 #ifndef YF_CFGUPCAT
@@ -241,7 +243,9 @@ template <class C>
 void launch_irb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using G = typename C::G;
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
-    irb_kernel<C><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.skip, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, g.headn);
+    const int total = B * tx * ty;
+    const int grid = total < g.nsm * C::MINB ? total : g.nsm * C::MINB;     // persistent: every CTA resident, loops over tiles
+    irb_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.skip, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total, g.headn);
 }
 template <class C>
 cudaError_t init_irb() { return cudaFuncSetAttribute(irb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
@@ -538,6 +542,12 @@ static void build_plan(yf_ctx* ctx) {
     }
 }
 
+static void set_sm_count(yf_ctx* ctx) {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    for (Group& g : ctx->groups) g.a.nsm = nsm;
+}
+
 extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors, int max_batch, int H, int W) {
     if (!out) { set_err(nullptr, "out is null"); return YF_ERR_ARG; }
     *out = nullptr;
@@ -575,6 +585,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
     int rc = alloc_all(ctx);
     if (rc != YF_OK) return fail(rc);
     build_plan(ctx);
+    set_sm_count(ctx);
     *out = ctx;
     return YF_OK;
 }
@@ -643,12 +654,21 @@ static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* hea
     if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
     if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
     if (!x || !head_large || !head_small) { set_err(&ctx->err, "null tensor pointer"); return YF_ERR_ARG; }
+    static const bool debug_sync = getenv("YF_DEBUG_SYNC") != nullptr;
     for (Group& g : ctx->groups) {
         GroupArgs a = g.a;
         if (!strcmp(g.name, "head_5")) a.y = head_small;
         if (!strcmp(g.name, "head_4")) a.y = head_large;
         g.launch(a, x, u8in, B, st);
         ctx->launches++;
+        if (debug_sync) {   // YF_DEBUG_SYNC=1: attribute a device fault to the group that raised it
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e != cudaSuccess) {
+                set_err(&ctx->err, "group '%s' failed: %s", g.name, cudaGetErrorString(e));
+                return YF_ERR_CUDA;
+            }
+        }
     }
     CU(cudaGetLastError());
     return YF_OK;

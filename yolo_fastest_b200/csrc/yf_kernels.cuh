@@ -51,6 +51,37 @@ __device__ __forceinline__ void copy_f4(float* __restrict__ dst, const float* __
     for (int i = threadIdx.x * 4; i < n; i += NT * 4) st4(dst + i, __ldg(reinterpret_cast<const float4*>(src + i)));
 }
 
+// ---- async-proxy primitives (sm_90+/sm_100a): mbarrier, TMA tensor tiles, bulk copies ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 4-byte cp.async with zero fill (src_bytes = 0 writes zeros and does not touch src): halo tiles of a planar
+// [C][H][W] tensor start 1-2 floats left of a 16-byte boundary, which rules out the tensor-tile form of TMA
+// (cp.async.bulk.tensor faults on sm_100a when the innermost start coordinate is not 16-byte aligned —
+// tools/selftest/tma_selftest.cu), so tiles are staged with LDGSTS and only the weight blocks use bulk TMA.
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both 16B aligned), completion on an mbarrier.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // Load an [nch][RH][RW] rectangle (zero outside the image, zero in the pad columns >= RW) of a
 // planar image into smem [nch][RH][RWS]. src points at channel 0 of the image.
 template <int RH, int RW, int RWS, int NT>
@@ -67,6 +98,32 @@ __device__ __forceinline__ void load_rect(float* __restrict__ dst, const float* 
         if (c < nch_valid && j < RW && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win)
             v = __ldg(src + ((size_t)c * Hin + gy) * Win + gx);
         dst[idx] = v;
+    }
+}
+
+// Asynchronous form of load_rect: warps walk (channel, row) pairs, lanes walk columns, every element is one
+// zero-filling 4-byte cp.async. The caller commits the group and waits (cp_async_wait_all + __syncthreads) before use.
+template <int RH, int RW, int RWS, int NT>
+__device__ __forceinline__ void load_rect_async(float* __restrict__ dst, const float* __restrict__ src, int nch, int nch_valid,
+                                                int Hin, int Win, int iy0, int ix0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = NT / 32;
+    for (int row = warp; row < nch * RH; row += NW) {
+        const int c = row / RH;
+        const int r = row - c * RH;
+        const int gy = iy0 + r;
+        const bool rowok = c < nch_valid && (unsigned)gy < (unsigned)Hin;
+        const float* srow = src + ((size_t)c * Hin + (rowok ? gy : 0)) * Win;
+        float* drow = dst + row * RWS;
+#pragma unroll
+        for (int j0 = 0; j0 < RWS; j0 += 32) {
+            const int j = j0 + lane;
+            if (j < RWS) {
+                const int gx = ix0 + j;
+                const bool ok = rowok && j < RW && (unsigned)gx < (unsigned)Win;
+                cp_async4(drow + j, ok ? srow + gx : src, ok ? 4 : 0);
+            }
+        }
     }
 }
 
@@ -316,136 +373,190 @@ struct IrbCfg {
     static constexpr int CB = OFF_W2 + MC * COUT;              // floats per chunk block
     static constexpr int OFF_B2 = NCHUNK * CB;
     static constexpr int OFF_WH = OFF_B2 + COUT;             // head weights [COUT][headp], then bias [headp] (runtime headn)
-    static constexpr int XS = EXPAND ? CIN * G::IPIX : 0;
-    static constexpr int ES = MC * G::IPIX;
-    static constexpr int DS = MC * G::OPIX;
-    static constexpr int ACT = cmax(XS + ES + DS, HEADN > 0 ? COUT * G::OPIX : 0);
-    static constexpr int SMEM_FLOATS = ACT + 2 * CB;
+    // shared memory (floats); every region starts 128B aligned
+    static constexpr int XS1 = EXPAND ? rup(CIN * G::IPIX, 32) : 0;   // one input halo tile [CIN][IH][IWS]
+    static constexpr int XS = 2 * XS1;                                   // double buffered: the next tile is prefetched
+    static constexpr int ES = rup(MC * G::IPIX, 32);
+    static constexpr int DS = rup(MC * G::OPIX, 32);
+    static constexpr int ACT = cmax(XS + ES + DS, HEADN > 0 ? rup(COUT * G::OPIX, 32) : 0);
+    static constexpr int WS1 = rup(CB, 32);
+    static constexpr int SMEM_FLOATS = ACT + 2 * WS1;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+    static constexpr int XBOX_C = EXPAND ? CIN : MC;            // channels staged per tile load
     static constexpr int NPG3 = G::OPIX / 4, NCG3 = COUT / PN3;
     static constexpr int IPT = cdiv(NPG3 * NCG3, NT);
     static_assert(MC % 4 == 0 && COUT % 4 == 0 && CB % 4 == 0, "alignment");
     static_assert(!RES || (CIN == COUT && S_ == 1 && EXPAND), "residual needs same shape");
-    static_assert(EXPAND || CMID == CIN, "dw-first groups have CMID == CIN");
+    static_assert(EXPAND || (CMID == CIN && CIN % MC == 0), "dw-first groups have CMID == CIN, a multiple of MC");
     static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
 };
 
+// Persistent CTAs (grid <= #SM x MINB) loop over tiles. While a tile is computed, the input halo tile of the NEXT
+// tile (cp.async into the other X buffer) and the weight block of the NEXT mid-channel chunk (cp.async.bulk ->
+// mbarrier, double buffered) are in flight, so no warp waits on a global load in steady state.
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ skip, const float* __restrict__ wts,
-           int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y, int headn) {
+           int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y, int total_tiles, int headn) {
     using G = typename C::G;
     constexpr int NT = C::NT;
-    extern __shared__ __align__(16) float smem[];
-    float* Xs = smem;
-    float* Es = Xs + C::XS;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bars[2];     // weight buffers
+    float* Xs0 = smem;
+    float* Es = smem + C::XS;
     float* Ds = Es + C::ES;
     float* Ws = smem + C::ACT;
+    const int tid = threadIdx.x;
 
-    const TileId t = tile_id(tiles_x, tiles_y);
-    const int oy0 = t.ty * G::TH, ox0 = t.tx * G::TW;
-    const int iy0 = oy0 * G::S - G::P, ix0 = ox0 * G::S - G::P;
-    const float* xb = x + (size_t)t.b * C::CIN * Hin * Win;
+    auto tile_origin = [&](int tile, int& b, int& oy0, int& ox0) {
+        const int tx = tile % tiles_x;
+        const int r = tile / tiles_x;
+        oy0 = (r % tiles_y) * G::TH;
+        ox0 = tx * G::TW;
+        b = r / tiles_y;
+    };
+    // all threads: stage channels [c0, c0 + XBOX_C) of the tile's halo rectangle into dst (asynchronously)
+    auto stage_tile = [&](int tile, int c0, float* dst) {
+        int b, oy0, ox0;
+        tile_origin(tile, b, oy0, ox0);
+        load_rect_async<G::IH, G::IW, G::IWS, NT>(dst, x + ((size_t)b * C::CIN + c0) * Hin * Win, C::XBOX_C, C::CIN - c0, Hin, Win,
+                                                  oy0 * G::S - G::P, ox0 * G::S - G::P);
+        cp_async_commit();
+    };
+    auto issue_w = [&](int chunk, int buf) {      // one thread
+        mbar_expect_tx(&bars[buf], C::CB * 4);
+        bulk_load(Ws + buf * C::WS1, wts + (size_t)chunk * C::CB, C::CB * 4, &bars[buf]);
+    };
 
-    if (C::EXPAND) load_rect<G::IH, G::IW, G::IWS, NT>(Xs, xb, C::CIN, C::CIN, Hin, Win, iy0, ix0);
-    copy_f4<NT>(Ws, wts, C::CB);
-
-    float acc[C::IPT][C::PN3][4];
-#pragma unroll
-    for (int it = 0; it < C::IPT; ++it)
-#pragma unroll
-        for (int n = 0; n < C::PN3; ++n)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
-
-    for (int c = 0; c < C::NCHUNK; ++c) {
-        const float* Wc = Ws + (c & 1) * C::CB;
-        __syncthreads();   // chunk c weights (and Xs) visible; Es/Ds of chunk c-1 no longer read
-        if (c + 1 < C::NCHUNK) copy_f4<NT>(Ws + ((c + 1) & 1) * C::CB, wts + (size_t)(c + 1) * C::CB, C::CB);
-        if (C::EXPAND) {
-            float* sk = C::DUAL ? skip + ((size_t)t.b * C::CMID + c * C::MC) * Hin * Win : nullptr;
-            pw_halo<G, C::CIN, C::MC, C::PN1, NT, C::DUAL>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win,
-                                                           sk, C::CMID - c * C::MC);
-        } else {
-            load_rect<G::IH, G::IW, G::IWS, NT>(Es, xb + (size_t)c * C::MC * Hin * Win, C::MC, C::CIN - c * C::MC,
-                                                Hin, Win, iy0, ix0);
-        }
-        __syncthreads();
-        dw_stage<G, C::MC, C::RH, NT>(Es, Wc + C::OFF_WD, Wc + C::OFF_BD, Ds);
-        __syncthreads();
-        pw_accum<G::OPIX, C::MC, C::COUT, C::PN3, C::IPT, NT>(Ds, Wc + C::OFF_W2, acc);
+    int tile = blockIdx.x;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tile < total_tiles) {
+        if (tid == 0) issue_w(0, 0);
+        stage_tile(tile, 0, C::EXPAND ? Xs0 : Es);
     }
 
-    const float* b2 = wts + C::OFF_B2;
-    if (C::HEADN > 0) __syncthreads();   // Ds/Es are about to be reused as the projected tile
-    float* Os = smem;                    // [COUT][OPIX] (HEADN > 0 only)
+    uint32_t q = 0;      // running chunk sequence number of this CTA (weight buffer q & 1, parity (q >> 1) & 1)
+    for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+        int tb, oy0, ox0;
+        tile_origin(tile, tb, oy0, ox0);
+        const int iy0 = oy0 * G::S - G::P, ix0 = ox0 * G::S - G::P;
+        float* Xs = Xs0 + (it & 1) * C::XS1;
+        const bool have_next = tile + (int)gridDim.x < total_tiles;
+
+        float acc[C::IPT][C::PN3][4];
 #pragma unroll
-    for (int it = 0; it < C::IPT; ++it) {
-        const int item = threadIdx.x + it * NT;
-        if (item < C::NPG3 * C::NCG3) {
-            const int cg = item / C::NPG3;
-            const int pg = item - cg * C::NPG3;
-            const int p0 = pg * 4;
-            const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
-            const int gy = oy0 + oy, gx0 = ox0 + ox;
+        for (int i = 0; i < C::IPT; ++i)
 #pragma unroll
-            for (int n = 0; n < C::PN3; ++n) {
-                const int ch = cg * C::PN3 + n;
-                const float b = __ldg(b2 + ch);
-                float v[4];
+            for (int n = 0; n < C::PN3; ++n)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = acc[it][n][i] + b;
-                if (C::RES) {
-                    const float* xr = Xs + ch * G::IPIX + (oy + G::P) * G::IWS + ox + G::P;
+                for (int j = 0; j < 4; ++j) acc[i][n][j] = 0.f;
+
+        for (int c = 0; c < C::NCHUNK; ++c, ++q) {
+            const int wbuf = (C::NCHUNK == 1) ? 0 : (int)(q & 1);
+            const float* Wc = Ws + wbuf * C::WS1;
+            if (!C::EXPAND || c == 0) cp_async_wait_all();   // this thread's share of the staged tile / E chunk has landed
+            __syncthreads();   // (A) staged data visible to all; everything of the previous chunk / tile has been consumed
+            if (tid == 0 && C::NCHUNK > 1 && (c + 1 < C::NCHUNK || have_next)) issue_w(c + 1 < C::NCHUNK ? c + 1 : 0, (int)((q + 1) & 1));
+            if (C::EXPAND && c == 0 && have_next) stage_tile(tile + gridDim.x, 0, Xs0 + ((it + 1) & 1) * C::XS1);
+            if (C::NCHUNK > 1) mbar_wait(&bars[wbuf], (q >> 1) & 1);
+            else if (it == 0) mbar_wait(&bars[0], 0);
+            if (C::EXPAND) {
+                float* sk = C::DUAL ? skip + ((size_t)tb * C::CMID + c * C::MC) * Hin * Win : nullptr;
+                pw_halo<G, C::CIN, C::MC, C::PN1, NT, C::DUAL>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win,
+                                                               sk, C::CMID - c * C::MC);
+                __syncthreads();   // (B) E complete
+            }
+            dw_stage<G, C::MC, C::RH, NT>(Es, Wc + C::OFF_WD, Wc + C::OFF_BD, Ds);
+            __syncthreads();   // (C) D complete, E free
+            if (!C::EXPAND) {
+                // the next E chunk (next channel chunk of this tile, or chunk 0 of the next tile) flies during the 1x1 below;
+                // a head epilogue reuses the E region, so there chunk 0 of the next tile is staged after it
+                if (c + 1 < C::NCHUNK) stage_tile(tile, (c + 1) * C::MC, Es);
+                else if (have_next && C::HEADN == 0) stage_tile(tile + gridDim.x, 0, Es);
+            }
+            pw_accum<G::OPIX, C::MC, C::COUT, C::PN3, C::IPT, NT>(Ds, Wc + C::OFF_W2, acc);
+        }
+
+        const float* b2 = wts + C::OFF_B2;
+        if (C::HEADN > 0) __syncthreads();   // Ds/Es are about to be reused as the projected tile
+        float* Os = smem;                    // [COUT][OPIX] (HEADN > 0 only)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] += xr[i];     // out += residual, no ReLU after (yolo_fastest.py:65)
-                }
-                if (C::RELU_OUT) {
+        for (int i = 0; i < C::IPT; ++i) {
+            const int item = tid + i * NT;
+            if (item < C::NPG3 * C::NCG3) {
+                const int cg = item / C::NPG3;
+                const int pg = item - cg * C::NPG3;
+                const int p0 = pg * 4;
+                const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+                const int gy = oy0 + oy, gx0 = ox0 + ox;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
-                }
-                if (C::HEADN > 0) {
-                    st4(Os + ch * G::OPIX + p0, make_float4(v[0], v[1], v[2], v[3]));
-                } else if (gy < Hout) {
-                    store_px4(y + (((size_t)t.b * C::COUT + ch) * Hout + gy) * Wout, gx0, Wout, v);
+                for (int n = 0; n < C::PN3; ++n) {
+                    const int ch = cg * C::PN3 + n;
+                    const float b = __ldg(b2 + ch);
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = acc[i][n][j] + b;
+                    if (C::RES) {
+                        const float* xr = Xs + ch * G::IPIX + (oy + G::P) * G::IWS + ox + G::P;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] += xr[j];     // out += residual, no ReLU after (yolo_fastest.py:65)
+                    }
+                    if (C::RELU_OUT) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (C::HEADN > 0) {
+                        st4(Os + ch * G::OPIX + p0, make_float4(v[0], v[1], v[2], v[3]));
+                    } else if (gy < Hout) {
+                        store_px4(y + (((size_t)tb * C::COUT + ch) * Hout + gy) * Wout, gx0, Wout, v);
+                    }
                 }
             }
         }
-    }
-    if (C::HEADN > 0) {
-        // biased 1x1 head conv (yolo_fastest.py:138,148) straight from the projected tile in smem;
-        // head weights [COUT][HEADP] are read through L1 (warp-broadcast).
-        __syncthreads();
-        const int headp = (headn + 3) & ~3;
-        const float* Wh = wts + C::OFF_WH;
-        const float* bh = Wh + C::COUT * headp;
-        constexpr int NPG = G::OPIX / 4;
-        const int NCGH = headp / 4;
-        for (int item = threadIdx.x; item < NPG * NCGH; item += NT) {
-            const int cg = item / NPG;
-            const int pg = item - cg * NPG;
-            const int p0 = pg * 4;
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bh + cg * 4));
-            float a[4][4] = {{bb.x, bb.x, bb.x, bb.x}, {bb.y, bb.y, bb.y, bb.y}, {bb.z, bb.z, bb.z, bb.z}, {bb.w, bb.w, bb.w, bb.w}};
+        if (C::HEADN > 0) {
+            // biased 1x1 head conv (yolo_fastest.py:138,148) straight from the projected tile in smem;
+            // head weights [COUT][headp] are read through L1 (warp-broadcast).
+            __syncthreads();
+            const int headp = (headn + 3) & ~3;
+            const float* Wh = wts + C::OFF_WH;
+            const float* bh = Wh + C::COUT * headp;
+            constexpr int NPG = G::OPIX / 4;
+            const int NCGH = headp / 4;
+            for (int item = tid; item < NPG * NCGH; item += NT) {
+                const int cg = item / NPG;
+                const int pg = item - cg * NPG;
+                const int p0 = pg * 4;
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bh + cg * 4));
+                float a[4][4] = {{bb.x, bb.x, bb.x, bb.x}, {bb.y, bb.y, bb.y, bb.y}, {bb.z, bb.z, bb.z, bb.z}, {bb.w, bb.w, bb.w, bb.w}};
 #pragma unroll 8
-            for (int k = 0; k < C::COUT; ++k) {
-                const float4 ov = ld4(Os + k * G::OPIX + p0);
-                const float4 w = __ldg(reinterpret_cast<const float4*>(Wh + k * headp + cg * 4));
-                const float o4[4] = {ov.x, ov.y, ov.z, ov.w};
-                const float w4[4] = {w.x, w.y, w.z, w.w};
+                for (int k = 0; k < C::COUT; ++k) {
+                    const float4 ov = ld4(Os + k * G::OPIX + p0);
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(Wh + k * headp + cg * 4));
+                    const float o4[4] = {ov.x, ov.y, ov.z, ov.w};
+                    const float w4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                    for (int qq = 0; qq < 4; ++qq)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) a[q][i] = fmaf(w4[q], o4[i], a[q][i]);
-            }
-            const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
-            const int gy = oy0 + oy, gx0 = ox0 + ox;
-            if (gy < Hout) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int ch = cg * 4 + q;
-                    if (ch < headn) store_px4(y + (((size_t)t.b * headn + ch) * Hout + gy) * Wout, gx0, Wout, a[q]);
+                        for (int j = 0; j < 4; ++j) a[qq][j] = fmaf(w4[qq], o4[j], a[qq][j]);
                 }
+                const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+                const int gy = oy0 + oy, gx0 = ox0 + ox;
+                if (gy < Hout) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int ch = cg * 4 + qq;
+                        if (ch < headn) store_px4(y + (((size_t)tb * headn + ch) * Hout + gy) * Wout, gx0, Wout, a[qq]);
+                    }
+                }
+            }
+            if (have_next) {
+                __syncthreads();           // the projected tile (aliasing E) has been consumed
+                stage_tile(tile + gridDim.x, 0, Es);
             }
         }
     }
@@ -481,7 +592,7 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
             int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y) {
     using G = typename C::G;
     constexpr int NT = C::NT;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* Rs = smem;
     float* Xs = Rs + C::RS;
     float* Es = Xs + C::XS;
@@ -609,7 +720,7 @@ dense_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __
              int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y) {
     using G = typename C::G;
     constexpr int NT = C::NT;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* Xs = smem;
     float* Es = Xs + C::XS;
     float* Ds = Es + C::ES;
@@ -730,7 +841,7 @@ template <class C>
 __global__ void __launch_bounds__(C::NT)
 pw_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts, int HW, int tiles) {
     constexpr int NT = C::NT;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* Xs = smem;
     float* Ws = Xs + C::K * C::PIXT;
     const int b = blockIdx.x / tiles;
@@ -815,7 +926,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB)
 upcat_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __restrict__ low /*[B,96,H/2,W/2]*/,
              float* __restrict__ y /*[B,96,H,W]*/, const float* __restrict__ wts, int H, int W, int tiles_x, int tiles_y) {
     constexpr int NT = C::NT;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* Ps = smem;
     float* Us = Ps + C::PS;
     float* Sc = Us + C::US;
