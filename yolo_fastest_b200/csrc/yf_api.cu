@@ -97,7 +97,8 @@ void set_err(std::string* dst, const char* fmt, ...) {
 // context
 // ---------------------------------------------------------------------------------------------
 struct GroupArgs {
-    int nsm = 148;               // SM count (persistent grids)
+    int nsm = 148;               // SM count
+    int resident = 148;          // persistent grid = CTAs that are co-resident on the device for this group's kernel
     const float* x = nullptr;    // input activation
     const float* x2 = nullptr;   // second input (upcat: low-res tensor)
     float* y = nullptr;          // output activation (or head)
@@ -108,6 +109,7 @@ struct GroupArgs {
 };
 
 struct Group {
+    int (*occupancy)() = nullptr;                       // resident CTAs per SM of the group's kernel (persistent groups)
     const char* name;                                   // reference attribute producing the group's output
     void (*launch)(const GroupArgs&, const void* xin, bool u8in, int B, cudaStream_t);
     GroupArgs a;
@@ -165,19 +167,19 @@ struct yf_ctx {
 // ---------------------------------------------------------------------------------------------
 // every configuration can be overridden with -DYF_CFG...="..." (tools/tune.py builds variants that way)
 #ifndef YF_CFGSTEM
-#define YF_CFGSTEM StemCfg<8, 40, 256, 3>
+#define YF_CFGSTEM StemCfg<8, 80, 256, 2>
 #endif
 using CfgStem = YF_CFGSTEM;
 #ifndef YF_CFGRES1
-#define YF_CFGRES1 IrbCfg<4, 8, 4, 3, 1, 8, 40, 8, 4, 4, 8, 256, 3, true, true, false, false>
+#define YF_CFGRES1 IrbCfg<4, 8, 4, 3, 1, 8, 80, 8, 8, 4, 8, 256, 3, true, true, false, false>
 #endif
 using CfgRes1 = YF_CFGRES1;
 #ifndef YF_CFGDENSE
-#define YF_CFGDENSE DenseCfg<4, 40, 8, 128, 3>
+#define YF_CFGDENSE DenseCfg<8, 40, 4, 128, 3, 2>
 #endif
 using CfgDense = YF_CFGDENSE;
 #ifndef YF_CFGRES2
-#define YF_CFGRES2 IrbCfg<8, 32, 8, 3, 1, 16, 40, 8, 8, 4, 8, 256, 3, true, true, false, false>
+#define YF_CFGRES2 IrbCfg<8, 32, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 4, true, true, false, false>
 #endif
 using CfgRes2 = YF_CFGRES2;
 #ifndef YF_CFGDOWN2
@@ -185,11 +187,11 @@ using CfgRes2 = YF_CFGRES2;
 #endif
 using CfgDown2 = YF_CFGDOWN2;
 #ifndef YF_CFGRES3A
-#define YF_CFGRES3A IrbCfg<8, 48, 8, 3, 1, 8, 40, 8, 8, 4, 8, 128, 5, true, true, false, false>
+#define YF_CFGRES3A IrbCfg<8, 48, 8, 3, 1, 8, 40, 16, 8, 4, 8, 128, 4, true, true, false, false>
 #endif
 using CfgRes3a = YF_CFGRES3A;
 #ifndef YF_CFGWIDE3
-#define YF_CFGWIDE3 IrbCfg<8, 48, 16, 3, 1, 8, 40, 8, 8, 8, 8, 128, 4, true, false, false, false>
+#define YF_CFGWIDE3 IrbCfg<8, 48, 16, 3, 1, 8, 40, 24, 8, 8, 8, 256, 2, true, false, false, false>
 #endif
 using CfgWide3 = YF_CFGWIDE3;
 #ifndef YF_CFGRES3B
@@ -197,7 +199,7 @@ using CfgWide3 = YF_CFGWIDE3;
 #endif
 using CfgRes3b = YF_CFGRES3B;
 #ifndef YF_CFGDOWN3
-#define YF_CFGDOWN3 IrbCfg<16, 96, 24, 3, 2, 4, 40, 8, 8, 8, 4, 256, 2, true, false, false, false>
+#define YF_CFGDOWN3 IrbCfg<16, 96, 24, 3, 2, 4, 40, 16, 8, 8, 4, 256, 2, true, false, false, false>
 #endif
 using CfgDown3 = YF_CFGDOWN3;
 #ifndef YF_CFGRES4
@@ -205,7 +207,7 @@ using CfgDown3 = YF_CFGDOWN3;
 #endif
 using CfgRes4 = YF_CFGRES4;
 #ifndef YF_CFGDOWN4
-#define YF_CFGDOWN4 IrbCfg<24, 136, 48, 3, 2, 4, 20, 16, 8, 8, 4, 256, 2, true, false, true, true>
+#define YF_CFGDOWN4 IrbCfg<24, 136, 48, 3, 2, 2, 20, 16, 8, 8, 2, 128, 4, true, false, true, true>
 #endif
 using CfgDown4 = YF_CFGDOWN4;
 #ifndef YF_CFGRES5
@@ -217,7 +219,7 @@ using CfgRes5 = YF_CFGRES5;
 #endif
 using CfgPw52 = YF_CFGPW52;
 #ifndef YF_CFGNECKS1
-#define YF_CFGNECKS1 IrbCfg<96, 96, 128, 5, 1, 8, 20, 32, 4, 8, 4, 640, 1, false, false, false, false>
+#define YF_CFGNECKS1 IrbCfg<96, 96, 128, 5, 1, 8, 20, 48, 4, 8, 4, 640, 1, false, false, false, false>
 #endif
 using CfgNeckS1 = YF_CFGNECKS1;
 #ifndef YF_CFGNECKS2
@@ -225,15 +227,15 @@ using CfgNeckS1 = YF_CFGNECKS1;
 #endif
 using CfgNeckS2 = YF_CFGNECKS2;
 #ifndef YF_CFGUPCAT
-#define YF_CFGUPCAT UpCatCfg<8, 20, 16, 256, 2>
+#define YF_CFGUPCAT UpCatCfg<8, 20, 16, 4, 256, 2>
 #endif
 using CfgUpCat = YF_CFGUPCAT;
 #ifndef YF_CFGNECKL1
-#define YF_CFGNECKL1 IrbCfg<96, 96, 96, 5, 1, 8, 20, 32, 4, 8, 4, 256, 2, false, false, false, false>
+#define YF_CFGNECKL1 IrbCfg<96, 96, 96, 5, 1, 4, 40, 32, 4, 8, 4, 256, 2, false, false, false, false>
 #endif
 using CfgNeckL1 = YF_CFGNECKL1;
 #ifndef YF_CFGNECKL2
-#define YF_CFGNECKL2 IrbCfg<96, 96, 96, 5, 1, 8, 20, 32, 4, 8, 4, 256, 2, false, false, false, false, 1>
+#define YF_CFGNECKL2 IrbCfg<96, 96, 96, 5, 1, 4, 40, 32, 4, 8, 4, 256, 2, false, false, false, false, 1>
 #endif
 using CfgNeckL2 = YF_CFGNECKL2;
 
@@ -244,9 +246,20 @@ void launch_irb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using G = typename C::G;
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
     const int total = B * tx * ty;
-    const int grid = total < g.nsm * C::MINB ? total : g.nsm * C::MINB;     // persistent: every CTA resident, loops over tiles
+    const int grid = total < g.resident ? total : g.resident;     // persistent: every CTA resident, loops over tiles
     irb_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.skip, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total, g.headn);
 }
+template <class K>
+int occ_of(K kernel, int nt, int smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, nt, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+template <class C> int occ_irb() { return occ_of(irb_kernel<C>, C::NT, C::SMEM_BYTES); }
+int occ_stem() { return occ_of(stem_kernel<CfgStem, false>, CfgStem::NT, CfgStem::SMEM_BYTES); }
+int occ_dense() { return occ_of(dense_kernel<CfgDense>, CfgDense::NT, CfgDense::SMEM_BYTES); }
+int occ_upcat() { return occ_of(upcat_kernel<CfgUpCat>, CfgUpCat::NT, CfgUpCat::SMEM_BYTES); }
+
 template <class C>
 cudaError_t init_irb() { return cudaFuncSetAttribute(irb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
 
@@ -254,14 +267,18 @@ void launch_stem(const GroupArgs& g, const void* xin, bool u8in, int B, cudaStre
     using C = CfgStem;
     using G = C::G;
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
-    if (u8in) stem_kernel<C, true><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(xin, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty);
-    else stem_kernel<C, false><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(xin, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    if (u8in) stem_kernel<C, true><<<grid, C::NT, C::SMEM_BYTES, st>>>(xin, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
+    else stem_kernel<C, false><<<grid, C::NT, C::SMEM_BYTES, st>>>(xin, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
 }
 void launch_dense(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using C = CfgDense;
     using G = C::G;
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
-    dense_kernel<C><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    dense_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
 }
 void launch_pw52(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using C = CfgPw52;
@@ -272,7 +289,9 @@ void launch_pw52(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) 
 void launch_upcat(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using C = CfgUpCat;
     const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
-    upcat_kernel<C><<<B * tx * ty, C::NT, C::SMEM_BYTES, st>>>(g.x, g.x2, g.y, g.w, g.Hout, g.Wout, tx, ty);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    upcat_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.x2, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
 }
 
 // ---- packing -------------------------------------------------------------------------------
@@ -387,8 +406,8 @@ int64_t pack_upcat(std::vector<float>& out, const Folded& f) {
     float* o = out.data() + off;
     const float* w = f.w("conv4_1_1");    // [96][232]
     for (int n = 0; n < 96; ++n) {
-        for (int k = 0; k < 136; ++k) o[C::OFF_WA + k * 96 + n] = w[n * 232 + k];
-        for (int k = 0; k < 96; ++k) o[C::OFF_WB + k * 96 + n] = w[n * 232 + 136 + k];
+        for (int k = 0; k < 136; ++k) o[C::OFF_WAB + k * 96 + n] = w[n * 232 + k];                    // rows 136..CSP-1 stay zero
+        for (int k = 0; k < 96; ++k) o[C::OFF_WAB + (C::CSP + k) * 96 + n] = w[n * 232 + 136 + k];
         o[C::OFF_B + n] = f.b("conv4_1_1")[n];
     }
     const float* wt = f.w("deconv5_1");   // [cin 96][cout 96][2][2]
@@ -406,6 +425,7 @@ Group make_irb(const char* name, int out_ch) {
     Group g{};
     g.name = name;
     g.launch = &launch_irb<C>;
+    g.occupancy = &occ_irb<C>;
     g.out_ch = out_ch;
     return g;
 }
@@ -493,12 +513,12 @@ static void build_plan(yf_ctx* ctx) {
         G.push_back(g);
     };
     {
-        Group g{}; g.name = "conv1_4"; g.launch = &launch_stem; g.out_ch = 4;
+        Group g{}; g.name = "conv1_4"; g.launch = &launch_stem; g.occupancy = &occ_stem; g.out_ch = 4;
         g.a.Hin = H; g.a.Win = W; g.a.Hout = H / 2; g.a.Wout = W / 2;
         g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
     chain(make_irb<CfgRes1>("res1_1", 4), 2, 2);
-    { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense; g.out_ch = 8; chain(g, 2, 4); }
+    { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense; g.occupancy = &occ_dense; g.out_ch = 8; chain(g, 2, 4); }
     chain(make_irb<CfgRes2>("res2_1", 8), 4, 4);
     chain(make_irb<CfgRes2>("res2_2", 8), 4, 4);
     chain(make_irb<CfgDown2>("conv3_1", 8), 4, 8);
@@ -532,7 +552,7 @@ static void build_plan(yf_ctx* ctx) {
         hw(g, 32, 32); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
     {
-        Group g{}; g.name = "conv4_1_1"; g.launch = &launch_upcat; g.out_ch = 96;
+        Group g{}; g.name = "conv4_1_1"; g.launch = &launch_upcat; g.occupancy = &occ_upcat; g.out_ch = 96;
         hw(g, 16, 16); g.a.x = ctx->d_skip; g.a.x2 = conv5_2; g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
     chain(make_irb<CfgNeckL1>("conv4_1_3", 96), 16, 16);
@@ -545,7 +565,10 @@ static void build_plan(yf_ctx* ctx) {
 static void set_sm_count(yf_ctx* ctx) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    for (Group& g : ctx->groups) g.a.nsm = nsm;
+    for (Group& g : ctx->groups) {
+        g.a.nsm = nsm;
+        g.a.resident = nsm * (g.occupancy ? g.occupancy() : 1);
+    }
 }
 
 extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors, int max_batch, int H, int W) {

@@ -356,8 +356,9 @@ __device__ __forceinline__ TileId tile_id(int tiles_x, int tiles_y) {
 // headn = num_anchors * (5 + num_cls) given at run time.
 // ---------------------------------------------------------------------------------------------
 template <int CIN_, int CMID_, int COUT_, int KS_, int S_, int TH_, int TW_, int MC_, int PN1_, int PN3_, int RH_,
-          int NT_, int MINB_, bool EXPAND_, bool RES_, bool RELU_OUT_, bool DUAL_, int HEADN_ = 0>
+          int NT_, int MINB_, bool EXPAND_, bool RES_, bool RELU_OUT_, bool DUAL_, int HEADN_ = 0, int XBUF_ = 1>
 struct IrbCfg {
+    static constexpr int XBUF = XBUF_;   // input-tile buffers: 2 = next tile prefetched during the whole tile, 1 = during its last chunk
     static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_, MC = MC_, PN1 = PN1_, PN3 = PN3_, RH = RH_;
     static constexpr int NT = NT_, MINB = MINB_, HEADN = HEADN_;
     static constexpr bool EXPAND = EXPAND_, RES = RES_, RELU_OUT = RELU_OUT_, DUAL = DUAL_;
@@ -375,7 +376,7 @@ struct IrbCfg {
     static constexpr int OFF_WH = OFF_B2 + COUT;             // head weights [COUT][headp], then bias [headp] (runtime headn)
     // shared memory (floats); every region starts 128B aligned
     static constexpr int XS1 = EXPAND ? rup(CIN * G::IPIX, 32) : 0;   // one input halo tile [CIN][IH][IWS]
-    static constexpr int XS = 2 * XS1;                                   // double buffered: the next tile is prefetched
+    static constexpr int XS = XBUF * XS1;
     static constexpr int ES = rup(MC * G::IPIX, 32);
     static constexpr int DS = rup(MC * G::OPIX, 32);
     static constexpr int ACT = cmax(XS + ES + DS, HEADN > 0 ? rup(COUT * G::OPIX, 32) : 0);
@@ -389,6 +390,7 @@ struct IrbCfg {
     static_assert(!RES || (CIN == COUT && S_ == 1 && EXPAND), "residual needs same shape");
     static_assert(EXPAND || (CMID == CIN && CIN % MC == 0), "dw-first groups have CMID == CIN, a multiple of MC");
     static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
+    static_assert(XBUF == 1 || XBUF == 2, "one or two input-tile buffers");
 };
 
 // Persistent CTAs (grid <= #SM x MINB) loop over tiles. While a tile is computed, the input halo tile of the NEXT
@@ -445,7 +447,7 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
         int tb, oy0, ox0;
         tile_origin(tile, tb, oy0, ox0);
         const int iy0 = oy0 * G::S - G::P, ix0 = ox0 * G::S - G::P;
-        float* Xs = Xs0 + (it & 1) * C::XS1;
+        float* Xs = Xs0 + (C::XBUF == 2 ? (it & 1) * C::XS1 : 0);
         const bool have_next = tile + (int)gridDim.x < total_tiles;
 
         float acc[C::IPT][C::PN3][4];
@@ -462,14 +464,34 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
             if (!C::EXPAND || c == 0) cp_async_wait_all();   // this thread's share of the staged tile / E chunk has landed
             __syncthreads();   // (A) staged data visible to all; everything of the previous chunk / tile has been consumed
             if (tid == 0 && C::NCHUNK > 1 && (c + 1 < C::NCHUNK || have_next)) issue_w(c + 1 < C::NCHUNK ? c + 1 : 0, (int)((q + 1) & 1));
-            if (C::EXPAND && c == 0 && have_next) stage_tile(tile + gridDim.x, 0, Xs0 + ((it + 1) & 1) * C::XS1);
+            if (C::EXPAND && C::XBUF == 2 && c == 0 && have_next) stage_tile(tile + gridDim.x, 0, Xs0 + ((it + 1) & 1) * C::XS1);
+            if (C::RES && c == 0) {
+                // out = project(...) + x (yolo_fastest.py:65): start the accumulators from the residual so the input
+                // tile is dead after the last expand stage and its buffer can take the next tile
+#pragma unroll
+                for (int i = 0; i < C::IPT; ++i) {
+                    const int item = tid + i * NT;
+                    if (item < C::NPG3 * C::NCG3) {
+                        const int cg = item / C::NPG3;
+                        const int p0 = (item - cg * C::NPG3) * 4;
+                        const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+#pragma unroll
+                        for (int n = 0; n < C::PN3; ++n) {
+                            const float* xr = Xs + (cg * C::PN3 + n) * G::IPIX + (oy + G::P) * G::IWS + ox + G::P;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[i][n][j] = xr[j];
+                        }
+                    }
+                }
+            }
             if (C::NCHUNK > 1) mbar_wait(&bars[wbuf], (q >> 1) & 1);
             else if (it == 0) mbar_wait(&bars[0], 0);
             if (C::EXPAND) {
                 float* sk = C::DUAL ? skip + ((size_t)tb * C::CMID + c * C::MC) * Hin * Win : nullptr;
                 pw_halo<G, C::CIN, C::MC, C::PN1, NT, C::DUAL>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win,
                                                                sk, C::CMID - c * C::MC);
-                __syncthreads();   // (B) E complete
+                __syncthreads();   // (B) E complete; after the last chunk the input tile is dead
+                if (C::XBUF == 1 && c == C::NCHUNK - 1 && have_next) stage_tile(tile + gridDim.x, 0, Xs0);
             }
             dw_stage<G, C::MC, C::RH, NT>(Es, Wc + C::OFF_WD, Wc + C::OFF_BD, Ds);
             __syncthreads();   // (C) D complete, E free
@@ -501,11 +523,6 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
                     float v[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = acc[i][n][j] + b;
-                    if (C::RES) {
-                        const float* xr = Xs + ch * G::IPIX + (oy + G::P) * G::IWS + ox + G::P;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] += xr[j];     // out += residual, no ReLU after (yolo_fastest.py:65)
-                    }
                     if (C::RELU_OUT) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -579,6 +596,7 @@ struct StemCfg {
     static constexpr int OFF_W0 = 0, OFF_B0 = 72, OFF_W1 = 80, OFF_B1 = 144, OFF_WD = 152, OFF_BD = 224, OFF_W2 = 232, OFF_B2 = 264;
     static constexpr int WFLOATS = 268;
     static constexpr int RS = RH * RWS;
+    static constexpr int NPRE = cdiv(RS, NT_);
     static constexpr int XS = 8 * G::IPIX, ES = 8 * G::IPIX, DS = 8 * G::OPIX;
     static constexpr int SMEM_FLOATS = RS + XS + ES + DS + WFLOATS;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
@@ -589,34 +607,53 @@ struct StemCfg {
 template <class C, bool U8IN>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __restrict__ wts,
-            int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y) {
+            int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y, int total_tiles) {
     using G = typename C::G;
     constexpr int NT = C::NT;
+    constexpr int NPRE = C::NPRE;               // raw-tile elements per thread
     extern __shared__ __align__(128) float smem[];
     float* Rs = smem;
     float* Xs = Rs + C::RS;
     float* Es = Xs + C::XS;
     float* Ds = Es + C::ES;
     float* Ws = Ds + C::DS;
-    const TileId t = tile_id(tiles_x, tiles_y);
-    const int oy0 = t.ty * G::TH, ox0 = t.tx * G::TW;
-    const int iy0 = oy0 - 1, ix0 = ox0 - 1;            // halo origin in the H/2 map
-    const int ry0 = 2 * iy0 - 1, rx0 = 2 * ix0 - 1;    // raw origin (conv0: stride 2, pad 1)
-    // raw tile
-    for (int idx = threadIdx.x; idx < C::RS; idx += NT) {
-        const int r = idx / C::RWS, jj = idx - r * C::RWS;
-        const int j = jj < C::REW ? 2 * jj : 2 * (jj - C::REW) + 1;     // raw column held at split position jj
-        const int gy = ry0 + r, gx = rx0 + j;
-        float v = 0.f;
-        if (j < C::RW && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win) {
-            const size_t off = ((size_t)t.b * Hin + gy) * Win + gx;
-            if (U8IN) v = ((float)__ldg(reinterpret_cast<const unsigned char*>(xin) + off) - 128.0f) / 255.0f;
-            else v = __ldg(reinterpret_cast<const float*>(xin) + off);
+    // fetch this thread's share of a tile's raw rectangle into registers (normalising uint8 on the fly)
+    auto fetch_raw = [&](int tile, float (&pre)[NPRE]) {
+        const int tx = tile % tiles_x;
+        const int r0 = tile / tiles_x;
+        const int ry0 = 2 * ((r0 % tiles_y) * G::TH - 1) - 1, rx0 = 2 * (tx * G::TW - 1) - 1, b = r0 / tiles_y;
+#pragma unroll
+        for (int k = 0; k < NPRE; ++k) {
+            const int idx = threadIdx.x + k * NT;
+            const int r = idx / C::RWS, jj = idx - r * C::RWS;
+            const int j = jj < C::REW ? 2 * jj : 2 * (jj - C::REW) + 1;     // raw column held at split position jj
+            const int gy = ry0 + r, gx = rx0 + j;
+            float v = 0.f;
+            if (idx < C::RS && j < C::RW && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win) {
+                const size_t off = ((size_t)b * Hin + gy) * Win + gx;
+                if (U8IN) v = ((float)__ldg(reinterpret_cast<const unsigned char*>(xin) + off) - 128.0f) / 255.0f;
+                else v = __ldg(reinterpret_cast<const float*>(xin) + off);
+            }
+            pre[k] = v;
         }
-        Rs[idx] = v;
-    }
+    };
     for (int i = threadIdx.x; i < C::WFLOATS; i += NT) Ws[i] = __ldg(wts + i);
+    float pre[NPRE];
+    int tile = blockIdx.x;
+    if (tile < total_tiles) fetch_raw(tile, pre);
+    for (; tile < total_tiles; tile += gridDim.x) {
+    const int tx_ = tile % tiles_x;
+    const int r0_ = tile / tiles_x;
+    const int oy0 = (r0_ % tiles_y) * G::TH, ox0 = tx_ * G::TW, tb = r0_ / tiles_y;
+    const int iy0 = oy0 - 1, ix0 = ox0 - 1;            // halo origin in the H/2 map
+    __syncthreads();                                   // previous tile done with Rs/Xs/Es/Ds
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+        const int idx = threadIdx.x + k * NT;
+        if (idx < C::RS) Rs[idx] = pre[k];
+    }
     __syncthreads();
+    if (tile + (int)gridDim.x < total_tiles) fetch_raw(tile + gridDim.x, pre);   // lands while this tile is computed
     // conv0 over the halo tile: item = 4 consecutive halo pixels x 8 channels
     {
         constexpr int NPG = G::IPIX / 4;
@@ -679,11 +716,12 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
                 for (int n = 0; n < 4; ++n) {
                     const float b = Ws[C::OFF_B2 + n];
                     const float v[4] = {acc[it][n][0] + b, acc[it][n][1] + b, acc[it][n][2] + b, acc[it][n][3] + b};
-                    store_px4(y + (((size_t)t.b * 4 + n) * Hout + gy) * Wout, gx0, Wout, v);
+                    store_px4(y + (((size_t)tb * 4 + n) * Hout + gy) * Wout, gx0, Wout, v);
                 }
             }
         }
     }
+    }   // tile loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -694,9 +732,9 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
 // Packed weights: NCHUNK x { [W1: 4*MC][b1: MC][Wc: MC*3*3(dy)*(3 cg)*(3 dx * 8 n)] } then
 //                 [b9: 24][W3: 24*8 ([m][n])][b3: 8]
 // ---------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int MC_, int NT_, int MINB_>
+template <int TH_, int TW_, int MC_, int NT_, int MINB_, int PXI_ = 1>
 struct DenseCfg {
-    static constexpr int NT = NT_, MINB = MINB_, MC = MC_;
+    static constexpr int NT = NT_, MINB = MINB_, MC = MC_, PXI = PXI_;   // PXI pixel groups per thread share one weight fetch
     using G = Geo<3, 2, TH_, TW_>;
     static constexpr int CM = 24;
     static constexpr int NCHUNK = CM / MC;
@@ -704,119 +742,154 @@ struct DenseCfg {
     static constexpr int CB = OFF_WC + MC * 3 * 3 * 24;          // [c][dy][cg][dx][8]
     static constexpr int OFF_B9 = NCHUNK * CB, OFF_W3 = OFF_B9 + 24, OFF_B3 = OFF_W3 + 24 * 8;
     static constexpr int WFLOATS = OFF_B3 + 8;
-    static constexpr int XS = 4 * G::IPIX, ES = MC * G::IPIX, DS = 24 * G::OPIX;
-    static constexpr int SMEM_FLOATS = XS + ES + DS + WFLOATS;
+    static constexpr int XS = rup(4 * G::IPIX, 32);
+    static constexpr int ES = rup(cmax(MC * G::IPIX, 24 * G::OPIX), 32);   // E chunk; reused for the conv1_9 output D [24][OPIX]
+    static constexpr int SMEM_FLOATS = XS + ES + rup(WFLOATS, 32);
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
     static constexpr int NPG = G::OPIX / 4;
-    static constexpr int IPT9 = cdiv(NPG * 3, NT);     // conv1_9 items: px-groups x 3 channel groups of 8
+    static constexpr int PGT = NPG / PXI;              // conv1_9: thread = (channel group of 8) x (slot of PXI pixel groups)
+    static constexpr int IPT9 = PXI;
     static constexpr int IPT3 = cdiv(NPG * 2, NT);     // conv2_1 items: px-groups x 2 channel groups of 4
-    static_assert(CM % MC == 0 && MC % 4 == 0, "bad MC");
+    static_assert(CM % MC == 0 && MC % 4 == 0 && WFLOATS % 4 == 0, "bad MC");
+    static_assert(NPG % PXI == 0 && 3 * PGT <= NT, "conv1_9 thread mapping does not fit the CTA");
     static_assert(SMEM_BYTES <= 227 * 1024, "dense tile too large");
 };
 
+// Persistent: the 22 KB of weights are fetched once per CTA (one bulk copy); the 4-channel input halo tile of the next
+// tile is staged with cp.async as soon as the last expand stage of the current tile has consumed the buffer.
+// conv1_9 inner loop: for every (input channel, kernel row) the 3x8 weights are read once and applied to all of the
+// thread's pixel groups (IPT9 x 4 pixels x 8 output channels of accumulators).
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 dense_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts,
-             int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y) {
+             int Hin, int Win, int Hout, int Wout, int tiles_x, int tiles_y, int total_tiles) {
     using G = typename C::G;
     constexpr int NT = C::NT;
     extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t wbar;
     float* Xs = smem;
     float* Es = Xs + C::XS;
-    float* Ds = Es + C::ES;
-    float* Ws = Ds + C::DS;
-    const TileId t = tile_id(tiles_x, tiles_y);
-    const int oy0 = t.ty * G::TH, ox0 = t.tx * G::TW;
-    const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-    load_rect<G::IH, G::IW, G::IWS, NT>(Xs, x + (size_t)t.b * 4 * Hin * Win, 4, 4, Hin, Win, iy0, ix0);
-    copy_f4<NT>(Ws, wts, C::WFLOATS);
+    float* Ds = Es;                    // alias: D is written after the last chunk's conv has consumed E
+    float* Ws = Es + C::ES;
+    const int tid = threadIdx.x;
+    auto stage_tile = [&](int tile) {
+        const int tx = tile % tiles_x;
+        const int r = tile / tiles_x;
+        const int oy0 = (r % tiles_y) * G::TH, ox0 = tx * G::TW, b = r / tiles_y;
+        load_rect_async<G::IH, G::IW, G::IWS, NT>(Xs, x + (size_t)b * 4 * Hin * Win, 4, 4, Hin, Win, oy0 * 2 - 1, ox0 * 2 - 1);
+        cp_async_commit();
+    };
+    int tile = blockIdx.x;
+    if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tile < total_tiles) {
+        if (tid == 0) { mbar_expect_tx(&wbar, C::WFLOATS * 4); bulk_load(Ws, wts, C::WFLOATS * 4, &wbar); }
+        stage_tile(tile);
+    }
+    // conv1_9 thread geometry (fixed across tiles): channel group my_cg, pixel groups slot + i * PGT
+    const bool conv_on = tid < 3 * C::PGT;
+    const int my_cg = conv_on ? tid / C::PGT : 0;
+    const int my_slot = conv_on ? tid - my_cg * C::PGT : 0;
+    int it_row[C::IPT9], it_g[C::IPT9];
+#pragma unroll
+    for (int i = 0; i < C::IPT9; ++i) {
+        const int p0 = (my_slot + i * C::PGT) * 4;
+        it_row[i] = p0 / G::TW;
+        it_g[i] = (p0 - it_row[i] * G::TW) >> 2;
+    }
+    for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int tx = tile % tiles_x;
+        const int rr = tile / tiles_x;
+        const int oy0 = (rr % tiles_y) * G::TH, ox0 = tx * G::TW, tb = rr / tiles_y;
+        const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+        const bool have_next = tile + (int)gridDim.x < total_tiles;
 
-    float acc[C::IPT9][8][4];
+        float acc[C::IPT9][8][4];
 #pragma unroll
-    for (int it = 0; it < C::IPT9; ++it)
+        for (int i = 0; i < C::IPT9; ++i)
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
+            for (int n = 0; n < 8; ++n)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
+                for (int j = 0; j < 4; ++j) acc[i][n][j] = 0.f;
 
-    for (int c = 0; c < C::NCHUNK; ++c) {
-        const float* Wc = Ws + c * C::CB;
-        __syncthreads();
-        pw_halo<G, 4, C::MC, (C::MC % 8 == 0 ? 8 : 4), NT, false>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win, nullptr, 0);
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < C::IPT9; ++it) {
-            const int item = threadIdx.x + it * NT;
-            if (item < C::NPG * 3) {
-                const int cg = item / C::NPG;
-                const int pg = item - cg * C::NPG;
-                const int p0 = pg * 4;
-                const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
-                const float* ep = Es + (oy * 2) * G::IWS;
-                const float* wp = Wc + C::OFF_WC + cg * 24;
-#pragma unroll 2
+        for (int c = 0; c < C::NCHUNK; ++c) {
+            const float* Wc = Ws + c * C::CB;
+            if (c == 0) cp_async_wait_all();
+            __syncthreads();   // staged tile visible; E / D of the previous chunk / tile consumed
+            if (c == 0 && it == 0) mbar_wait(&wbar, 0);
+            pw_halo<G, 4, C::MC, (C::MC % 8 == 0 ? 8 : 4), NT, false>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win, nullptr, 0);
+            __syncthreads();
+            if (c == C::NCHUNK - 1 && have_next) stage_tile(tile + gridDim.x);     // X is dead: next tile flies during the conv
+            if (conv_on) {
+#pragma unroll 1
                 for (int m = 0; m < C::MC; ++m) {
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
-                        float v[9];
-                        load_window<G>(v, ep + m * G::IPIX + dy * G::IWS, ox >> 2);
-                        const float* w = wp + (m * 3 + dy) * 72;
+                        const float* w = Wc + C::OFF_WC + my_cg * 24 + (m * 3 + dy) * 72;
+                        float w8[3][8];
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
                             const float4 wa = ld4(w + dx * 8);
                             const float4 wb = ld4(w + dx * 8 + 4);
-                            const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                            w8[dx][0] = wa.x; w8[dx][1] = wa.y; w8[dx][2] = wa.z; w8[dx][3] = wa.w;
+                            w8[dx][4] = wb.x; w8[dx][5] = wb.y; w8[dx][6] = wb.z; w8[dx][7] = wb.w;
+                        }
 #pragma unroll
-                            for (int n = 0; n < 8; ++n)
+                        for (int i = 0; i < C::IPT9; ++i) {
+                            float v[9];
+                            load_window<G>(v, Es + m * G::IPIX + (it_row[i] * 2 + dy) * G::IWS, it_g[i]);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) acc[it][n][i] = fmaf(w8[n], v[2 * i + dx], acc[it][n][i]);
+                            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                                for (int n = 0; n < 8; ++n)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) acc[i][n][j] = fmaf(w8[dx][n], v[2 * j + dx], acc[i][n][j]);
                         }
                     }
                 }
             }
         }
-    }
-    // conv1_9 bias + ReLU -> Ds[24][OPIX]
+        __syncthreads();       // every thread is done reading E before D overwrites it
+        // conv1_9 bias + ReLU -> Ds[24][OPIX]
+        if (conv_on) {
 #pragma unroll
-    for (int it = 0; it < C::IPT9; ++it) {
-        const int item = threadIdx.x + it * NT;
-        if (item < C::NPG * 3) {
-            const int cg = item / C::NPG;
-            const int pg = item - cg * C::NPG;
+            for (int i = 0; i < C::IPT9; ++i) {
+                const int pg = my_slot + i * C::PGT;
 #pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                const float b = Ws[C::OFF_B9 + cg * 8 + n];
-                st4(Ds + (cg * 8 + n) * G::OPIX + pg * 4,
-                    make_float4(fmaxf(acc[it][n][0] + b, 0.f), fmaxf(acc[it][n][1] + b, 0.f),
-                                fmaxf(acc[it][n][2] + b, 0.f), fmaxf(acc[it][n][3] + b, 0.f)));
+                for (int n = 0; n < 8; ++n) {
+                    const float b = Ws[C::OFF_B9 + my_cg * 8 + n];
+                    st4(Ds + (my_cg * 8 + n) * G::OPIX + pg * 4,
+                        make_float4(fmaxf(acc[i][n][0] + b, 0.f), fmaxf(acc[i][n][1] + b, 0.f),
+                                    fmaxf(acc[i][n][2] + b, 0.f), fmaxf(acc[i][n][3] + b, 0.f)));
+                }
             }
         }
-    }
-    __syncthreads();
-    float a3[C::IPT3][4][4];
+        __syncthreads();
+        float a3[C::IPT3][4][4];
 #pragma unroll
-    for (int it = 0; it < C::IPT3; ++it)
+        for (int i = 0; i < C::IPT3; ++i)
 #pragma unroll
-        for (int n = 0; n < 4; ++n)
+            for (int n = 0; n < 4; ++n)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a3[it][n][i] = 0.f;
-    pw_accum<G::OPIX, 24, 8, 4, C::IPT3, NT>(Ds, Ws + C::OFF_W3, a3);
+                for (int j = 0; j < 4; ++j) a3[i][n][j] = 0.f;
+        pw_accum<G::OPIX, 24, 8, 4, C::IPT3, NT>(Ds, Ws + C::OFF_W3, a3);
 #pragma unroll
-    for (int it = 0; it < C::IPT3; ++it) {
-        const int item = threadIdx.x + it * NT;
-        if (item < C::NPG * 2) {
-            const int cg = item / C::NPG;
-            const int pg = item - cg * C::NPG;
-            const int p0 = pg * 4;
-            const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
-            const int gy = oy0 + oy, gx0 = ox0 + ox;
-            if (gy < Hout) {
+        for (int i = 0; i < C::IPT3; ++i) {
+            const int item = tid + i * NT;
+            if (item < C::NPG * 2) {
+                const int cg = item / C::NPG;
+                const int pg = item - cg * C::NPG;
+                const int p0 = pg * 4;
+                const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+                const int gy = oy0 + oy, gx0 = ox0 + ox;
+                if (gy < Hout) {
 #pragma unroll
-                for (int n = 0; n < 4; ++n) {
-                    const int ch = cg * 4 + n;
-                    const float b = Ws[C::OFF_B3 + ch];
-                    const float v[4] = {a3[it][n][0] + b, a3[it][n][1] + b, a3[it][n][2] + b, a3[it][n][3] + b};
-                    store_px4(y + (((size_t)t.b * 8 + ch) * Hout + gy) * Wout, gx0, Wout, v);
+                    for (int n = 0; n < 4; ++n) {
+                        const int ch = cg * 4 + n;
+                        const float b = Ws[C::OFF_B3 + ch];
+                        const float v[4] = {a3[i][n][0] + b, a3[i][n][1] + b, a3[i][n][2] + b, a3[i][n][3] + b};
+                        store_px4(y + (((size_t)tb * 8 + ch) * Hout + gy) * Wout, gx0, Wout, v);
+                    }
                 }
             }
         }
@@ -899,161 +972,184 @@ pw_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __res
 //            pixels — a 1x1 GEMM over parent pixels with one weight set per output parity — kept in smem;
 //   phase B  out = relu(Wa . skip + Wb . U + b), K streamed in chunks: skip channels staged from HBM,
 //            up channels read straight from the smem U tile.
-// Packed weights: [Wa: 136*96 ([k][n])][Wb: 96*96 ([k][n])][b: 96][Wt: 96(c) * 4(py*2+px) * 96(m)][bt: 96]
+// Packed weights: [Wab: (144 + 96) * 96 ([k][n]; rows 136..143 zero)][b: 96][Wt: 96(c) * 4(py*2+px) * 96(m)][bt: 96]
+// Persistent; all weight chunks arrive by bulk copy (double buffered, mbarrier), the parent tile, the skip-channel
+// chunks and the next tile's parent tile by cp.async, so both phases compute while their next operands fly.
 // ---------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int KC_, int NT_, int MINB_>
+template <int TH_, int TW_, int KC_, int KCA_, int NT_, int MINB_>
 struct UpCatCfg {
-    static constexpr int TH = TH_, TW = TW_, KC = KC_, NT = NT_, MINB = MINB_;
+    static constexpr int TH = TH_, TW = TW_, KC = KC_, KCA = KCA_, NT = NT_, MINB = MINB_;
     static constexpr int CS = 136, CU = 96, N = 96;
     static constexpr int OPIX = TH * TW, PH = TH / 2, PW = TW / 2, PPIX = PH * PW;
-    static constexpr int OFF_WA = 0, OFF_WB = CS * N, OFF_B = OFF_WB + CU * N, OFF_WT = OFF_B + N, OFF_BT = OFF_WT + CU * 4 * CU;
+    static constexpr int CSP = rup(CS, KC);
+    static constexpr int OFF_WAB = 0, OFF_B = (CSP + CU) * N, OFF_WT = OFF_B + N, OFF_BT = OFF_WT + CU * 4 * CU;
     static constexpr int WFLOATS = OFF_BT + CU;
     static constexpr int PN = 8;
     static constexpr int IPT = cdiv((OPIX / 4) * (N / PN), NT);               // phase B items per thread
     static constexpr int IPTA = cdiv((PPIX / 4) * 4 * (CU / PN), NT);         // phase A items per thread
-    static constexpr int CSP = rup(CS, KC);
-    static constexpr int PS = CU * PPIX;            // parent tile [96][PPIX]
-    static constexpr int US = CU * OPIX;            // upsampled tile [96][OPIX]
-    static constexpr int SCR = cmax(KC * 4 * CU, KC * OPIX + KC * N);   // phase A weight chunk | phase B (skip chunk + weight rows)
-    static constexpr int SMEM_FLOATS = PS + US + SCR;
+    static constexpr int NCA = CU / KCA;                                      // phase A chunks
+    static constexpr int NCS = CSP / KC, NCB = NCS + CU / KC;                 // phase B chunks (skip part, total)
+    static constexpr int PS = rup(CU * PPIX, 32);   // parent tile [96][PPIX]
+    static constexpr int US = rup(CU * OPIX, 32);   // upsampled tile [96][OPIX]
+    static constexpr int WB1 = rup(cmax(KCA * 4 * CU, KC * N), 32);    // one weight buffer
+    static constexpr int BS1 = rup(KC * OPIX, 32);                      // one skip-chunk buffer
+    static constexpr int SMEM_FLOATS = PS + US + 2 * WB1 + 2 * BS1;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
-    static_assert(TH % 2 == 0 && TW % 4 == 0 && CU % KC == 0 && KC % 4 == 0 && PPIX % 4 == 0, "bad upcat tiling");
+    static_assert(TH % 2 == 0 && TW % 4 == 0 && CU % KC == 0 && CU % KCA == 0 && KC % 4 == 0 && PPIX % 4 == 0, "bad upcat tiling");
     static_assert(SMEM_BYTES <= 227 * 1024, "upcat tile too large");
 };
 
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 upcat_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __restrict__ low /*[B,96,H/2,W/2]*/,
-             float* __restrict__ y /*[B,96,H,W]*/, const float* __restrict__ wts, int H, int W, int tiles_x, int tiles_y) {
+             float* __restrict__ y /*[B,96,H,W]*/, const float* __restrict__ wts, int H, int W, int tiles_x, int tiles_y, int total_tiles) {
     constexpr int NT = C::NT;
     extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bars[2];
     float* Ps = smem;
     float* Us = Ps + C::PS;
-    float* Sc = Us + C::US;
-    const TileId t = tile_id(tiles_x, tiles_y);
-    const int oy0 = t.ty * C::TH, ox0 = t.tx * C::TW;
+    float* Wb = Us + C::US;            // 2 weight buffers
+    float* Bs = Wb + 2 * C::WB1;       // 2 skip-chunk buffers
+    const int tid = threadIdx.x;
     const int Hl = H / 2, Wl = W / 2;
-    for (int idx = threadIdx.x; idx < C::PS; idx += NT) {
-        const int c = idx / C::PPIX, p = idx - c * C::PPIX;
-        const int py = p / C::PW, px = p - py * C::PW;
-        const int gy = oy0 / 2 + py, gx = ox0 / 2 + px;
-        Ps[idx] = (gy < Hl && gx < Wl) ? __ldg(low + (((size_t)t.b * C::CU + c) * Hl + gy) * Wl + gx) : 0.f;
+    auto origin = [&](int tile, int& b, int& oy0, int& ox0) {
+        const int tx = tile % tiles_x;
+        const int r = tile / tiles_x;
+        oy0 = (r % tiles_y) * C::TH; ox0 = tx * C::TW; b = r / tiles_y;
+    };
+    auto stage_parent = [&](int tile) {
+        int b, oy0, ox0;
+        origin(tile, b, oy0, ox0);
+        load_rect_async<C::PH, C::PW, C::PW, NT>(Ps, low + (size_t)b * C::CU * Hl * Wl, C::CU, C::CU, Hl, Wl, oy0 / 2, ox0 / 2);
+        cp_async_commit();
+    };
+    auto stage_skip = [&](int tile, int chunk, float* dst) {
+        int b, oy0, ox0;
+        origin(tile, b, oy0, ox0);
+        load_rect_async<C::TH, C::TW, C::TW, NT>(dst, skip + ((size_t)b * C::CS + chunk * C::KC) * H * W, C::KC, C::CS - chunk * C::KC,
+                                                 H, W, oy0, ox0);
+        cp_async_commit();
+    };
+    // weight chunk sequence of one tile: NCA phase-A blocks of Wt, then NCB phase-B row blocks of Wab
+    auto issue_w = [&](int s, int buf) {     // one thread
+        const float* src = s < C::NCA ? wts + C::OFF_WT + (size_t)s * C::KCA * 4 * C::CU : wts + C::OFF_WAB + (size_t)(s - C::NCA) * C::KC * C::N;
+        const uint32_t bytes = (s < C::NCA ? C::KCA * 4 * C::CU : C::KC * C::N) * 4;
+        mbar_expect_tx(&bars[buf], bytes);
+        bulk_load(Wb + buf * C::WB1, src, bytes, &bars[buf]);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tile < total_tiles) {
+        if (tid == 0) issue_w(0, 0);
+        stage_parent(tile);
     }
-    // ---- phase A: item = 4 consecutive parent pixels x one output parity x 8 up channels ----------------
-    {
-        constexpr int NPG = C::PPIX / 4, NCG = C::CU / C::PN;
-        float u[C::IPTA][C::PN][4];
+    uint32_t q = 0;
+    for (; tile < total_tiles; tile += gridDim.x) {
+        int tb, oy0, ox0;
+        origin(tile, tb, oy0, ox0);
+        const bool have_next = tile + (int)gridDim.x < total_tiles;
+        // ---- phase A: item = 4 consecutive parent pixels x one output parity x 8 up channels ----------------
+        {
+            constexpr int NPG = C::PPIX / 4, NCG = C::CU / C::PN;
+            float u[C::IPTA][C::PN][4];
 #pragma unroll
-        for (int it = 0; it < C::IPTA; ++it)
+            for (int it = 0; it < C::IPTA; ++it)
 #pragma unroll
-            for (int n = 0; n < C::PN; ++n)
+                for (int n = 0; n < C::PN; ++n)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) u[it][n][i] = 0.f;
-        for (int c0 = 0; c0 < C::CU; c0 += C::KC) {
-            __syncthreads();                                           // previous chunk consumed (first: Ps visible)
-            copy_f4<NT>(Sc, wts + C::OFF_WT + (size_t)c0 * 4 * C::CU, C::KC * 4 * C::CU);
-            __syncthreads();
+                    for (int i = 0; i < 4; ++i) u[it][n][i] = 0.f;
+            for (int ca = 0; ca < C::NCA; ++ca, ++q) {
+                if (ca == 0) cp_async_wait_all();                        // parent tile landed
+                __syncthreads();                                         // previous chunk / tile consumed
+                if (ca == 0) stage_skip(tile, 0, Bs);                    // first skip chunk flies during phase A
+                if (tid == 0) issue_w(ca + 1, (int)((q + 1) & 1));       // ca + 1 == NCA is the first phase-B block
+                mbar_wait(&bars[q & 1], (q >> 1) & 1);
+                const float* Wt = Wb + (q & 1) * C::WB1;
+#pragma unroll
+                for (int it = 0; it < C::IPTA; ++it) {
+                    const int item = tid + it * NT;
+                    if (item < NPG * 4 * NCG) {
+                        const int pg = item % NPG;
+                        const int par = (item / NPG) & 3;
+                        const int cg = item / (NPG * 4);
+                        const float* pp = Ps + (size_t)ca * C::KCA * C::PPIX + pg * 4;
+                        const float* wp = Wt + par * C::CU + cg * C::PN;
+#pragma unroll
+                        for (int k = 0; k < C::KCA; ++k) {
+                            const float4 pv = ld4(pp + k * C::PPIX);
+                            const float p4[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                            for (int n4 = 0; n4 < C::PN / 4; ++n4) {
+                                const float4 w = ld4(wp + k * 4 * C::CU + n4 * 4);
+                                const float w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) u[it][n4 * 4 + qq][i] = fmaf(w4[qq], p4[i], u[it][n4 * 4 + qq][i]);
+                            }
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int it = 0; it < C::IPTA; ++it) {
-                const int item = threadIdx.x + it * NT;
+                const int item = tid + it * NT;
                 if (item < NPG * 4 * NCG) {
                     const int pg = item % NPG;
                     const int par = (item / NPG) & 3;
                     const int cg = item / (NPG * 4);
-                    const float* pp = Ps + (size_t)c0 * C::PPIX + pg * 4;
-                    const float* wp = Sc + par * C::CU + cg * C::PN;
-#pragma unroll 4
-                    for (int k = 0; k < C::KC; ++k) {
-                        const float4 pv = ld4(pp + k * C::PPIX);
-                        const float p4[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
-                        for (int n4 = 0; n4 < C::PN / 4; ++n4) {
-                            const float4 w = ld4(wp + k * 4 * C::CU + n4 * 4);
-                            const float w4[4] = {w.x, w.y, w.z, w.w};
+                    for (int n = 0; n < C::PN; ++n) {
+                        const int mch = cg * C::PN + n;
+                        const float b = __ldg(wts + C::OFF_BT + mch);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) u[it][n4 * 4 + q][i] = fmaf(w4[q], p4[i], u[it][n4 * 4 + q][i]);
+                        for (int i = 0; i < 4; ++i) {
+                            const int p = pg * 4 + i;
+                            const int py = p / C::PW, px = p - py * C::PW;
+                            Us[mch * C::OPIX + (2 * py + (par >> 1)) * C::TW + 2 * px + (par & 1)] = fmaxf(u[it][n][i] + b, 0.f);
                         }
                     }
                 }
             }
         }
+        // ---- phase B: 1x1 over the concatenation, K in blocks of KC ------------------------------------------
+        float acc[C::IPT][C::PN][4];
 #pragma unroll
-        for (int it = 0; it < C::IPTA; ++it) {
-            const int item = threadIdx.x + it * NT;
-            if (item < NPG * 4 * NCG) {
-                const int pg = item % NPG;
-                const int par = (item / NPG) & 3;
-                const int cg = item / (NPG * 4);
+        for (int it = 0; it < C::IPT; ++it)
 #pragma unroll
-                for (int n = 0; n < C::PN; ++n) {
-                    const int mch = cg * C::PN + n;
-                    const float b = __ldg(wts + C::OFF_BT + mch);
+            for (int n = 0; n < C::PN; ++n)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int p = pg * 4 + i;
-                        const int py = p / C::PW, px = p - py * C::PW;
-                        Us[mch * C::OPIX + (2 * py + (par >> 1)) * C::TW + 2 * px + (par & 1)] = fmaxf(u[it][n][i] + b, 0.f);
+                for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
+        for (int cb = 0; cb < C::NCB; ++cb, ++q) {
+            if (cb <= C::NCS) cp_async_wait_all();     // skip chunk cb (and, at cb == 0, nothing else pending) has landed
+            __syncthreads();                           // previous block consumed; at cb == 0: U complete, parent tile dead
+            if (cb == 0 && have_next) stage_parent(tile + gridDim.x);
+            if (cb + 1 < C::NCS) stage_skip(tile, cb + 1, Bs + ((cb + 1) & 1) * C::BS1);
+            if (tid == 0 && (cb + 1 < C::NCB || have_next)) issue_w(cb + 1 < C::NCB ? C::NCA + cb + 1 : 0, (int)((q + 1) & 1));
+            mbar_wait(&bars[q & 1], (q >> 1) & 1);
+            const float* src = cb < C::NCS ? Bs + (cb & 1) * C::BS1 : Us + (size_t)(cb - C::NCS) * C::KC * C::OPIX;
+            pw_accum<C::OPIX, C::KC, C::N, C::PN, C::IPT, NT>(src, Wb + (q & 1) * C::WB1, acc);
+        }
+        constexpr int NPG = C::OPIX / 4;
+#pragma unroll
+        for (int it = 0; it < C::IPT; ++it) {
+            const int item = tid + it * NT;
+            if (item < NPG * (C::N / C::PN)) {
+                const int cg = item / NPG;
+                const int pg = item - cg * NPG;
+                const int p0 = pg * 4;
+                const int oy = p0 / C::TW, ox = p0 - oy * C::TW;
+                const int gy = oy0 + oy, gx0 = ox0 + ox;
+                if (gy < H) {
+#pragma unroll
+                    for (int n = 0; n < C::PN; ++n) {
+                        const int ch = cg * C::PN + n;
+                        const float b = __ldg(wts + C::OFF_B + ch);
+                        const float v[4] = {fmaxf(acc[it][n][0] + b, 0.f), fmaxf(acc[it][n][1] + b, 0.f),
+                                            fmaxf(acc[it][n][2] + b, 0.f), fmaxf(acc[it][n][3] + b, 0.f)};
+                        store_px4(y + (((size_t)tb * C::N + ch) * H + gy) * W, gx0, W, v);
                     }
-                }
-            }
-        }
-    }
-    // ---- phase B: 1x1 over the concatenation, K in chunks ------------------------------------------------
-    float acc[C::IPT][C::PN][4];
-#pragma unroll
-    for (int it = 0; it < C::IPT; ++it)
-#pragma unroll
-        for (int n = 0; n < C::PN; ++n)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[it][n][i] = 0.f;
-    float* Bs = Sc;
-    float* Ws = Sc + C::KC * C::OPIX;
-    constexpr int NCH_S = C::CSP / C::KC, NCH_U = C::CU / C::KC;
-    for (int c = 0; c < NCH_S + NCH_U; ++c) {
-        __syncthreads();     // previous chunk fully consumed (first: phase A done, Us visible)
-        if (c < NCH_S) {
-            const int k0 = c * C::KC;
-            for (int idx = threadIdx.x; idx < C::KC * C::OPIX; idx += NT) {
-                const int k = idx / C::OPIX, p = idx - k * C::OPIX;
-                const int oy = p / C::TW, ox = p - oy * C::TW;
-                const int gy = oy0 + oy, gx = ox0 + ox;
-                float v = 0.f;
-                if (k0 + k < C::CS && gy < H && gx < W) v = __ldg(skip + (((size_t)t.b * C::CS + k0 + k) * H + gy) * W + gx);
-                Bs[idx] = v;
-            }
-            for (int idx = threadIdx.x; idx < C::KC * C::N; idx += NT) {
-                const int k = idx / C::N;
-                Ws[idx] = (k0 + k < C::CS) ? __ldg(wts + C::OFF_WA + (size_t)k0 * C::N + idx) : 0.f;
-            }
-            __syncthreads();
-            pw_accum<C::OPIX, C::KC, C::N, C::PN, C::IPT, NT>(Bs, Ws, acc);
-        } else {
-            const int m0 = (c - NCH_S) * C::KC;
-            copy_f4<NT>(Ws, wts + C::OFF_WB + (size_t)m0 * C::N, C::KC * C::N);
-            __syncthreads();
-            pw_accum<C::OPIX, C::KC, C::N, C::PN, C::IPT, NT>(Us + (size_t)m0 * C::OPIX, Ws, acc);
-        }
-    }
-    constexpr int NPG = C::OPIX / 4;
-#pragma unroll
-    for (int it = 0; it < C::IPT; ++it) {
-        const int item = threadIdx.x + it * NT;
-        if (item < NPG * (C::N / C::PN)) {
-            const int cg = item / NPG;
-            const int pg = item - cg * NPG;
-            const int p0 = pg * 4;
-            const int oy = p0 / C::TW, ox = p0 - oy * C::TW;
-            const int gy = oy0 + oy, gx0 = ox0 + ox;
-            if (gy < H) {
-#pragma unroll
-                for (int n = 0; n < C::PN; ++n) {
-                    const int ch = cg * C::PN + n;
-                    const float b = __ldg(wts + C::OFF_B + ch);
-                    const float v[4] = {fmaxf(acc[it][n][0] + b, 0.f), fmaxf(acc[it][n][1] + b, 0.f),
-                                        fmaxf(acc[it][n][2] + b, 0.f), fmaxf(acc[it][n][3] + b, 0.f)};
-                    store_px4(y + (((size_t)t.b * C::N + ch) * H + gy) * W, gx0, W, v);
                 }
             }
         }
