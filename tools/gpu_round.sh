@@ -1,17 +1,24 @@
 #!/bin/bash
-# One GPU-box session: per-group parity report, GPU test suite, smoke, bench. Everything lands in gpurun_out/.
+# One GPU-box session: GPU test suite, smoke, bench (ours + reference arm), ncu launch list. Everything lands in gpurun_out/.
 mkdir -p gpurun_out
+rm -f gpurun_out/summary.txt
 nvidia-smi > gpurun_out/nvidia-smi.txt 2>&1
-for cfg in 256x320 512x640 stress; do
-  timeout 600 python tools/check_forward.py $cfg 2 > gpurun_out/check_$cfg.log 2>&1
-  echo "check $cfg exit $?" >> gpurun_out/summary.txt
-done
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/summary.txt
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/summary.txt
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
+echo "bench ref exit $?" >> gpurun_out/summary.txt
+timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench exit $?" >> gpurun_out/summary.txt
+timeout 900 python bench.py --res 256x320 --no-cpu-baseline > gpurun_out/bench_256.log 2> gpurun_out/bench_256.err
+echo "bench 256 exit $?" >> gpurun_out/summary.txt
+timeout 600 python bench.py --batch 1 --steps 200 --warmup 20 --no-cpu-baseline > gpurun_out/bench_b1.log 2> gpurun_out/bench_b1.err
+echo "bench b1 exit $?" >> gpurun_out/summary.txt
+# every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
+timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"irb_kernel|dense_kernel|stem_kernel|upcat_kernel|pw_kernel|post_kernel" -c 400 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+echo "ncu launches exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
-tail -5 gpurun_out/check_256x320.log gpurun_out/pytest.log gpurun_out/smoke.log
-tail -c 1500 gpurun_out/bench.log
+tail -n 3 gpurun_out/pytest.log gpurun_out/smoke.log
