@@ -165,6 +165,16 @@ int yf_detect_host(yf_ctx* ctx, const float* x_host, int B, const yf_post_params
 int yf_detect_host_u8(yf_ctx* ctx, const uint8_t* u8_host, int B, const yf_post_params* p,
                       yf_det* out_host, int32_t* counts_host, int32_t* status_host, void* stream);
 
+/* Asynchronous, double-buffered form of yf_detect_host_u8 for serving loops: two slots (0, 1), each with its own
+ * device staging and result buffers. yf_detect_submit_u8 enqueues the H2D copy on an internal copy stream and
+ * the detection + D2H of the results on an internal compute stream and returns immediately; yf_detect_wait
+ * blocks until the slot's results are in out_host / counts_host / status_host. Submitting batch i+1 into the
+ * other slot before waiting for batch i overlaps its H2D copy with the compute of batch i. The host buffers
+ * must stay valid (and should be pinned) until the wait returns. */
+int yf_detect_submit_u8(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
+                        yf_det* out_host, int32_t* counts_host, int32_t* status_host);
+int yf_detect_wait(yf_ctx* ctx, int slot);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 
 /* Kernels launched by this ctx since creation (the bench's gpu_launches evidence). */

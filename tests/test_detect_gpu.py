@@ -100,3 +100,21 @@ def test_fused_u8_equals_float_path(gold):
     x = torch.cat([O.preprocess_gray(u) for u in u8], 0).cuda()
     b = det.post_process.postprocess_batch(det.model(x))
     assert a == b
+
+
+def test_async_double_buffered_serving_loop(gold):
+    """yf_detect_submit_u8 / yf_detect_wait: batches in flight in both slots give the blocking call's results."""
+    g = gold.res["256x320"]
+    det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_256x320"), yf.config_for("256x320"), None)
+    u8 = torch.from_numpy(g["u8"].copy())
+    batches = [u8[0:8].contiguous().pin_memory(), u8[8:16].contiguous().pin_memory(), u8[12:20].contiguous().pin_memory()]
+    want = [det.detect_batch(b.numpy(), max_det=16) for b in batches]
+    det.submit_batch(batches[0], 0, max_det=16)
+    got = []
+    for i in range(3):
+        if i + 1 < 3:
+            det.submit_batch(batches[i + 1], (i + 1) & 1, max_det=16)
+        got.append(det.collect(i & 1))
+    assert got == want
+    with pytest.raises(yf.YfError):
+        det.submit_batch(g["u8"][:2], 0)            # not a host tensor

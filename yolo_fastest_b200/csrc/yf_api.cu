@@ -145,6 +145,15 @@ struct yf_ctx {
     int4* p_sbox = nullptr;
     int32_t* p_order = nullptr;
     unsigned char* p_alive = nullptr;
+    // double-buffered asynchronous host path (yf_detect_submit_u8 / yf_detect_wait)
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    unsigned char* sl_u8[2] = {nullptr, nullptr};
+    yf_det* sl_out[2] = {nullptr, nullptr};
+    int sl_out_cap[2] = {0, 0};
+    int32_t* sl_counts[2] = {nullptr, nullptr};
+    int32_t* sl_status[2] = {nullptr, nullptr};
+    cudaEvent_t sl_in[2] = {nullptr, nullptr}, sl_free[2] = {nullptr, nullptr}, sl_done[2] = {nullptr, nullptr};
+    bool sl_used[2] = {false, false};
     unsigned char* n_alive = nullptr;                   // yf_nms_sorted_* scratch
     int n_alive_cap = 0;
     int64_t launches = 0;
@@ -621,6 +630,14 @@ extern "C" void yf_destroy(yf_ctx* ctx) {
     cudaFree(ctx->d_out); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
     cudaFree(ctx->p_rec); cudaFree(ctx->p_conf); cudaFree(ctx->p_cls); cudaFree(ctx->p_sbox); cudaFree(ctx->p_order);
     cudaFree(ctx->p_alive); cudaFree(ctx->n_alive);
+    if (ctx->s_copy) {
+        cudaStreamSynchronize(ctx->s_copy); cudaStreamSynchronize(ctx->s_comp);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(ctx->sl_u8[i]); cudaFree(ctx->sl_out[i]); cudaFree(ctx->sl_counts[i]); cudaFree(ctx->sl_status[i]);
+            cudaEventDestroy(ctx->sl_in[i]); cudaEventDestroy(ctx->sl_free[i]); cudaEventDestroy(ctx->sl_done[i]);
+        }
+        cudaStreamDestroy(ctx->s_copy); cudaStreamDestroy(ctx->s_comp);
+    }
     delete ctx;
 }
 
@@ -903,6 +920,62 @@ extern "C" int yf_detect_host_u8(yf_ctx* ctx, const uint8_t* u8_host, int B, con
                                  int32_t* counts_host, int32_t* status_host, void* stream) {
     CTX_CHECK(ctx);
     return detect_host_impl(ctx, u8_host, true, B, p, out_host, counts_host, status_host, (cudaStream_t)stream);
+}
+
+// ---- asynchronous, double-buffered host path --------------------------------------------------------------
+static int slots_init(yf_ctx* ctx) {
+    if (ctx->s_copy) return YF_OK;
+    CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    const size_t npx = (size_t)ctx->max_batch * ctx->in_ch * ctx->H * ctx->W;
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&ctx->sl_u8[i], npx));
+        CU(cudaMalloc(&ctx->sl_counts[i], sizeof(int32_t) * ctx->max_batch));
+        CU(cudaMalloc(&ctx->sl_status[i], sizeof(int32_t) * ctx->max_batch));
+        CU(cudaEventCreateWithFlags(&ctx->sl_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->sl_free[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->sl_done[i], cudaEventDisableTiming));
+    }
+    return YF_OK;
+}
+
+extern "C" int yf_detect_submit_u8(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
+                                   yf_det* out_host, int32_t* counts_host, int32_t* status_host) {
+    CTX_CHECK(ctx);
+    if (slot < 0 || slot > 1 || !u8_host || !p || !out_host || !counts_host) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
+    if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
+    if (p->max_det < 1) { set_err(&ctx->err, "max_det must be >= 1"); return YF_ERR_ARG; }
+    CU(cudaSetDevice(ctx->device));
+    int rc = slots_init(ctx);
+    if (rc) return rc;
+    if (p->max_det > ctx->sl_out_cap[slot]) {
+        if (ctx->sl_used[slot]) CU(cudaEventSynchronize(ctx->sl_done[slot]));
+        if (ctx->sl_out[slot]) CU(cudaFree(ctx->sl_out[slot]));
+        ctx->sl_out[slot] = nullptr;
+        CU(cudaMalloc(&ctx->sl_out[slot], sizeof(yf_det) * (size_t)p->max_det * ctx->max_batch));
+        ctx->sl_out_cap[slot] = p->max_det;
+    }
+    const size_t npx = (size_t)B * ctx->in_ch * ctx->H * ctx->W;
+    if (ctx->sl_used[slot]) CU(cudaStreamWaitEvent(ctx->s_copy, ctx->sl_free[slot], 0));   // previous batch of this slot has been consumed
+    CU(cudaMemcpyAsync(ctx->sl_u8[slot], u8_host, npx, cudaMemcpyHostToDevice, ctx->s_copy));
+    CU(cudaEventRecord(ctx->sl_in[slot], ctx->s_copy));
+    CU(cudaStreamWaitEvent(ctx->s_comp, ctx->sl_in[slot], 0));
+    rc = detect_impl(ctx, ctx->sl_u8[slot], true, B, p, ctx->sl_out[slot], ctx->sl_counts[slot], ctx->sl_status[slot], ctx->s_comp);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->sl_free[slot], ctx->s_comp));
+    CU(cudaMemcpyAsync(out_host, ctx->sl_out[slot], sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CU(cudaMemcpyAsync(counts_host, ctx->sl_counts[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_comp));
+    if (status_host) CU(cudaMemcpyAsync(status_host, ctx->sl_status[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CU(cudaEventRecord(ctx->sl_done[slot], ctx->s_comp));
+    ctx->sl_used[slot] = true;
+    return YF_OK;
+}
+
+extern "C" int yf_detect_wait(yf_ctx* ctx, int slot) {
+    CTX_CHECK(ctx);
+    if (slot < 0 || slot > 1 || !ctx->sl_used[slot]) { set_err(&ctx->err, "slot %d has no submitted batch", slot); return YF_ERR_STATE; }
+    CU(cudaEventSynchronize(ctx->sl_done[slot]));
+    return YF_OK;
 }
 
 extern "C" int64_t yf_launch_count(const yf_ctx* ctx) { return ctx ? ctx->launches : -1; }

@@ -161,6 +161,7 @@ class Detect_YOLO:
                                               input_shape=self.input_shape, num_class=self.num_cls)
         self.colors = [[106, 90, 205], [199, 97, 20], [112, 128, 105]]
         self._pinned = {}
+        self._slots = {}
 
     # ---- host-side image handling (unchanged semantics, detect.py:107-139) ------------------------
     def _load_gray(self, img_path):
@@ -226,6 +227,43 @@ class Detect_YOLO:
         counts = pin_cnt.numpy()
         if (pin_st.numpy() & 1).any():
             raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
+        dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
+        res = [dets[b, :min(int(counts[b]), max_det)].copy() for b in range(B)]
+        return res if raw else [_rows_from_dets(d) for d in res]
+
+    def submit_batch(self, u8_pinned, slot, max_det=64):
+        """Asynchronous form of detect_batch for serving loops (yf_detect_submit_u8): `u8_pinned` is a pinned host
+        uint8 tensor [B, H, W] that must stay untouched until `collect(slot)`. Submitting the next batch into the
+        other slot before collecting this one overlaps its host-to-device copy with this batch's compute."""
+        if not (isinstance(u8_pinned, torch.Tensor) and u8_pinned.dtype == torch.uint8 and u8_pinned.is_contiguous()
+                and not u8_pinned.is_cuda):
+            raise _lib.YfError("submit_batch takes a contiguous host uint8 tensor (pinned for asynchronous copies)")
+        B, H, W = u8_pinned.shape
+        if [H, W] != list(self.input_shape[0:2]):
+            raise _lib.YfError("images are %dx%d, the network input is %s" % (H, W, self.input_shape[0:2]))
+        ctx = self.model.context(self.device, H, W, B)
+        st = self._slots.get(slot)
+        if st is None or st[0] != (B, max_det):
+            st = ((B, max_det), torch.empty((B, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8).pin_memory(),
+                  torch.empty((B,), dtype=torch.int32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory())
+            self._slots[slot] = st
+        _, pin_out, pin_cnt, pin_st = st
+        p = self.post_process._params(_lib.MODE_DETECT, max_det)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().yf_detect_submit_u8(ctx.handle, slot, u8_pinned.data_ptr(), B, C.byref(p), pin_out.data_ptr(),
+                                                     pin_cnt.data_ptr(), pin_st.data_ptr()), ctx.handle)
+        self._slot_ref = getattr(self, "_slot_ref", {})
+        self._slot_ref[slot] = u8_pinned          # keep the input alive until collected
+
+    def collect(self, slot, raw=False):
+        """Wait for the batch submitted into `slot` and return its per-image detections."""
+        ctx = self.model._ctx
+        (B, max_det), pin_out, pin_cnt, pin_st = self._slots[slot]
+        _lib.check(_lib.lib().yf_detect_wait(ctx.handle, slot), ctx.handle)
+        self._slot_ref.pop(slot, None)
+        if (pin_st.numpy() & 1).any():
+            raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
+        counts = pin_cnt.numpy()
         dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
         res = [dets[b, :min(int(counts[b]), max_det)].copy() for b in range(B)]
         return res if raw else [_rows_from_dets(d) for d in res]
