@@ -227,7 +227,7 @@ def main():
     def step_device():
         out, counts, status = det.detect_device(x_dev, args.max_det)
         if world > 1:
-            gather_detections(out, counts, n_total, dst=0)
+            gather_detections(out, counts, n_total, dst=0, to_host=False)     # one NCCL gather, results stay on rank 0's device
         return counts
 
     def step_e2e():
@@ -266,13 +266,24 @@ def main():
     u8b = [u8, synthetic_u8(B, H, W, 2000 + rank).pin_memory()]
 
     def run_e2e(nsteps):
-        det.submit_batch(u8b[0], 0, max_det=args.max_det)
-        rows = None
+        if world == 1:
+            det.submit_batch(u8b[0], 0, max_det=args.max_det)
+            rows = None
+            for i in range(nsteps):
+                if i + 1 < nsteps:
+                    det.submit_batch(u8b[(i + 1) & 1], (i + 1) & 1, max_det=args.max_det)
+                rows = det.collect(i & 1, raw=True)
+            return rows
+        # N > 1: every rank runs the same double-buffered loop with its results left on the device, returns its slab to
+        # rank 0 with one NCCL gather per step, and rank 0 reads the whole job's detections back to the host
+        pend = det.submit_batch_device(u8b[0], 0, max_det=args.max_det)
+        res = None
         for i in range(nsteps):
-            if i + 1 < nsteps:
-                det.submit_batch(u8b[(i + 1) & 1], (i + 1) & 1, max_det=args.max_det)
-            rows = det.collect(i & 1, raw=True)
-        return rows
+            nxt = det.submit_batch_device(u8b[(i + 1) & 1], (i + 1) & 1, max_det=args.max_det) if i + 1 < nsteps else None
+            det.wait(i & 1)
+            res = gather_detections(pend[0], pend[1], n_total, dst=0, to_host=True)
+            pend = nxt
+        return res
 
     run_e2e(3)
     barrier()

@@ -174,6 +174,11 @@ int yf_detect_host_u8(yf_ctx* ctx, const uint8_t* u8_host, int B, const yf_post_
 int yf_detect_submit_u8(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
                         yf_det* out_host, int32_t* counts_host, int32_t* status_host);
 int yf_detect_wait(yf_ctx* ctx, int slot);
+/* Same submission with the results left in caller-owned DEVICE buffers (out_dev [B][max_det], counts_dev [B],
+ * status_dev [B] or NULL) — for multi-GPU jobs that return their slabs to rank 0 with a collective. After
+ * yf_detect_wait the buffers are complete and may be read from any stream. */
+int yf_detect_submit_u8_dev(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
+                            yf_det* out_dev, int32_t* counts_dev, int32_t* status_dev);
 
 /* ---- introspection ---------------------------------------------------------------------- */
 

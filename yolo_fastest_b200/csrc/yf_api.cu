@@ -939,9 +939,23 @@ static int slots_init(yf_ctx* ctx) {
     return YF_OK;
 }
 
+static int submit_impl(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
+                       yf_det* out_host, int32_t* counts_host, int32_t* status_host, bool out_on_device);
+
 extern "C" int yf_detect_submit_u8(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
                                    yf_det* out_host, int32_t* counts_host, int32_t* status_host) {
     CTX_CHECK(ctx);
+    return submit_impl(ctx, slot, u8_host, B, p, out_host, counts_host, status_host, false);
+}
+
+extern "C" int yf_detect_submit_u8_dev(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
+                                       yf_det* out_dev, int32_t* counts_dev, int32_t* status_dev) {
+    CTX_CHECK(ctx);
+    return submit_impl(ctx, slot, u8_host, B, p, out_dev, counts_dev, status_dev, true);
+}
+
+static int submit_impl(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
+                       yf_det* out_host, int32_t* counts_host, int32_t* status_host, bool out_on_device) {
     if (slot < 0 || slot > 1 || !u8_host || !p || !out_host || !counts_host) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
     if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
     if (p->max_det < 1) { set_err(&ctx->err, "max_det must be >= 1"); return YF_ERR_ARG; }
@@ -960,12 +974,18 @@ extern "C" int yf_detect_submit_u8(yf_ctx* ctx, int slot, const uint8_t* u8_host
     CU(cudaMemcpyAsync(ctx->sl_u8[slot], u8_host, npx, cudaMemcpyHostToDevice, ctx->s_copy));
     CU(cudaEventRecord(ctx->sl_in[slot], ctx->s_copy));
     CU(cudaStreamWaitEvent(ctx->s_comp, ctx->sl_in[slot], 0));
-    rc = detect_impl(ctx, ctx->sl_u8[slot], true, B, p, ctx->sl_out[slot], ctx->sl_counts[slot], ctx->sl_status[slot], ctx->s_comp);
-    if (rc) return rc;
-    CU(cudaEventRecord(ctx->sl_free[slot], ctx->s_comp));
-    CU(cudaMemcpyAsync(out_host, ctx->sl_out[slot], sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, ctx->s_comp));
-    CU(cudaMemcpyAsync(counts_host, ctx->sl_counts[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_comp));
-    if (status_host) CU(cudaMemcpyAsync(status_host, ctx->sl_status[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_comp));
+    if (out_on_device) {    // results go straight into the caller's device buffers (e.g. to be gathered with NCCL)
+        rc = detect_impl(ctx, ctx->sl_u8[slot], true, B, p, out_host, counts_host, status_host ? status_host : ctx->sl_status[slot], ctx->s_comp);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->sl_free[slot], ctx->s_comp));
+    } else {
+        rc = detect_impl(ctx, ctx->sl_u8[slot], true, B, p, ctx->sl_out[slot], ctx->sl_counts[slot], ctx->sl_status[slot], ctx->s_comp);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->sl_free[slot], ctx->s_comp));
+        CU(cudaMemcpyAsync(out_host, ctx->sl_out[slot], sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, ctx->s_comp));
+        CU(cudaMemcpyAsync(counts_host, ctx->sl_counts[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_comp));
+        if (status_host) CU(cudaMemcpyAsync(status_host, ctx->sl_status[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_comp));
+    }
     CU(cudaEventRecord(ctx->sl_done[slot], ctx->s_comp));
     ctx->sl_used[slot] = true;
     return YF_OK;

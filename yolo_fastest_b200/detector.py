@@ -255,6 +255,31 @@ class Detect_YOLO:
         self._slot_ref = getattr(self, "_slot_ref", {})
         self._slot_ref[slot] = u8_pinned          # keep the input alive until collected
 
+    def submit_batch_device(self, u8_pinned, slot, max_det=64):
+        """As submit_batch, but the results stay on the device: returns (dets uint8 [B, max_det, 56], counts int32 [B])
+        cuda tensors that are complete once `wait(slot)` has returned (multi-GPU jobs gather them with NCCL)."""
+        B, H, W = u8_pinned.shape
+        ctx = self.model.context(self.device, H, W, B)
+        key = ("dev", slot)
+        st = self._slots.get(key)
+        if st is None or st[0] != (B, max_det):
+            st = ((B, max_det), torch.empty((B, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8, device=self.device),
+                  torch.empty((B,), dtype=torch.int32, device=self.device))
+            self._slots[key] = st
+        _, out, cnt = st
+        p = self.post_process._params(_lib.MODE_DETECT, max_det)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().yf_detect_submit_u8_dev(ctx.handle, slot, u8_pinned.data_ptr(), B, C.byref(p), out.data_ptr(),
+                                                         cnt.data_ptr(), None), ctx.handle)
+        self._slot_ref = getattr(self, "_slot_ref", {})
+        self._slot_ref[slot] = u8_pinned
+        return out, cnt
+
+    def wait(self, slot):
+        ctx = self.model._ctx
+        _lib.check(_lib.lib().yf_detect_wait(ctx.handle, slot), ctx.handle)
+        self._slot_ref.pop(slot, None)
+
     def collect(self, slot, raw=False):
         """Wait for the batch submitted into `slot` and return its per-image detections."""
         ctx = self.model._ctx

@@ -20,34 +20,44 @@ def shard_range(n_items, rank, world_size):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_detections(dets, counts, n_total, dst=0, group=None):
-    """Gather per-rank detection slabs to `dst`.
+class _Buffers:
+    cache = {}
+
+
+def gather_detections(dets, counts, n_total, dst=0, group=None, to_host=True):
+    """Gather per-rank detection slabs to `dst` with ONE collective.
 
     dets:   uint8 tensor [B_local, max_det, 56] (yf_det records), counts: int32 tensor [B_local];
             both on the same device (cuda -> NCCL, cpu -> gloo).  Ranks may hold different B_local
-            (ragged shards from shard_range); slabs are padded to the largest shard for the collective.
-    Returns (dets [n_total, max_det] structured numpy array, counts [n_total]) on `dst`, (None, None) elsewhere.
+            (ragged shards from shard_range); slabs are padded to the largest shard and packed with their
+            counts into one [max_local, max_det*56 + 4] byte tensor for the collective.
+    Returns on `dst` (dets [n_total, max_det] structured numpy array, counts [n_total]) — or, with
+    to_host=False, the packed device tensors per rank (no synchronisation) — and (None, None) elsewhere.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     max_local = -(-n_total // world)
     max_det = dets.shape[1]
-    pad_d = torch.zeros((max_local, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8, device=dets.device)
-    pad_c = torch.zeros((max_local,), dtype=torch.int32, device=dets.device)
-    pad_d[:dets.shape[0]] = dets
-    pad_c[:counts.shape[0]] = counts
-    if rank == dst:
-        all_d = [torch.empty_like(pad_d) for _ in range(world)]
-        all_c = [torch.empty_like(pad_c) for _ in range(world)]
-    else:
-        all_d = all_c = None
-    dist.gather(pad_d, all_d, dst=dst, group=group)
-    dist.gather(pad_c, all_c, dst=dst, group=group)
+    row = max_det * _lib.DET_DTYPE.itemsize
+    key = (str(dets.device), max_local, max_det, world, rank == dst)
+    buf = _Buffers.cache.get(key)
+    if buf is None:
+        packed = torch.zeros((max_local, row + 4), dtype=torch.uint8, device=dets.device)
+        recv = [torch.empty_like(packed) for _ in range(world)] if rank == dst else None
+        buf = _Buffers.cache[key] = (packed, recv)
+    packed, recv = buf
+    nl = dets.shape[0]
+    packed[:nl, :row] = dets.reshape(nl, row)
+    packed[:nl, row:] = counts.view(torch.uint8).reshape(nl, 4)
+    dist.gather(packed, recv, dst=dst, group=group)
     if rank != dst:
         return None, None
+    if not to_host:
+        return recv, None
     out_d, out_c = [], []
     for r in range(world):
         lo, hi = shard_range(n_total, r, world)
-        out_d.append(all_d[r][:hi - lo].cpu().numpy().view(_lib.DET_DTYPE).reshape(hi - lo, max_det))
-        out_c.append(all_c[r][:hi - lo].cpu().numpy())
+        h = recv[r][:hi - lo].cpu().numpy()
+        out_d.append(np.ascontiguousarray(h[:, :row]).view(_lib.DET_DTYPE).reshape(hi - lo, max_det))
+        out_c.append(np.ascontiguousarray(h[:, row:]).view(np.int32).reshape(hi - lo))
     return np.concatenate(out_d, 0), np.concatenate(out_c, 0)
