@@ -14,6 +14,7 @@
 #include "../../include/yf.h"
 #include "yf_kernels.cuh"
 #include "yf_post.cuh"
+#include "yf_tc.cuh"
 
 using namespace yf;
 
@@ -154,6 +155,8 @@ struct yf_ctx {
     int32_t* sl_status[2] = {nullptr, nullptr};
     cudaEvent_t sl_in[2] = {nullptr, nullptr}, sl_free[2] = {nullptr, nullptr}, sl_done[2] = {nullptr, nullptr};
     bool sl_used[2] = {false, false};
+    // CUDA graphs of forward + head kernel on the library's own fixed buffers (small batches: launch latency dominates)
+    std::map<std::string, std::pair<cudaGraphExec_t, int>> graphs;    // key -> (executable graph, kernel launches inside)
     unsigned char* n_alive = nullptr;                   // yf_nms_sorted_* scratch
     int n_alive_cap = 0;
     int64_t launches = 0;
@@ -207,6 +210,14 @@ using CfgWide3 = YF_CFGWIDE3;
 #define YF_CFGRES3B IrbCfg<16, 96, 16, 3, 1, 8, 40, 16, 8, 8, 8, 256, 2, true, true, false, false>
 #endif
 using CfgRes3b = YF_CFGRES3B;
+// tensor-core (tcgen05, 3xTF32) variant for the wide residual blocks: IrbTcCfg<CIN, CMID, COUT, TH, TW, MC, RH, NT, RES>
+#ifndef YF_CFGRES3B_TC
+#define YF_CFGRES3B_TC IrbTcCfg<16, 96, 16, 8, 40, 16, 8, 256, true>
+#endif
+using CfgRes3bTc = YF_CFGRES3B_TC;
+#ifndef YF_USE_TC
+#define YF_USE_TC 0     // 1: res3_3..6 run on the tcgen05 kernel (correct, not yet faster than the FFMA engine; built as libyf_b200_tc.so)
+#endif
 #ifndef YF_CFGDOWN3
 #define YF_CFGDOWN3 IrbCfg<16, 96, 24, 3, 2, 4, 40, 16, 8, 8, 4, 256, 2, true, false, false, false>
 #endif
@@ -268,6 +279,18 @@ template <class C> int occ_irb() { return occ_of(irb_kernel<C>, C::NT, C::SMEM_B
 int occ_stem() { return occ_of(stem_kernel<CfgStem, false>, CfgStem::NT, CfgStem::SMEM_BYTES); }
 int occ_dense() { return occ_of(dense_kernel<CfgDense>, CfgDense::NT, CfgDense::SMEM_BYTES); }
 int occ_upcat() { return occ_of(upcat_kernel<CfgUpCat>, CfgUpCat::NT, CfgUpCat::SMEM_BYTES); }
+
+template <class C>
+void launch_irbtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using G = typename C::G;
+    const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    irbtc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+}
+template <class C> int occ_irbtc() { return occ_of(irbtc_kernel<C>, C::NT, C::SMEM_BYTES); }
+template <class C>
+cudaError_t init_irbtc() { return cudaFuncSetAttribute(irbtc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
 
 template <class C>
 cudaError_t init_irb() { return cudaFuncSetAttribute(irb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
@@ -344,6 +367,44 @@ int64_t pack_irb(std::vector<float>& out, const Folded& f, const std::string& n1
             for (int n = 0; n < headn; ++n) wh[k * headp + n] = f.w(nh)[n * C::COUT + k];
         for (int n = 0; n < headn; ++n) bh[n] = f.b(nh)[n];
     }
+    return off;
+}
+
+inline float tf32_rna_host(float v) {      // cvt.rna.tf32.f32: round to nearest (ties away) at 10 mantissa bits
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    memcpy(&v, &u, 4);
+    return v;
+}
+// weights of a tensor-core block: K-major core-matrix layout [n/8][k/4][n%8][k%4], split into hi = tf32(w) and lo = w - hi
+inline void put_kmajor_split(float* hi, float* lo, int n, int k, int K, float w) {
+    const int idx = ((n >> 3) * (K / 4) + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
+    const float h = tf32_rna_host(w);
+    hi[idx] = h;
+    lo[idx] = w - h;
+}
+
+template <class C>
+int64_t pack_irbtc(std::vector<float>& out, const Folded& f, const std::string& n1, const std::string& nd, const std::string& n2) {
+    pad4(out);
+    while (out.size() % 32) out.push_back(0.f);          // bulk copies and UMMA descriptors want 128-byte aligned blocks
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int c = 0; c < C::NCHUNK; ++c) {
+        float* cb = o + (int64_t)c * C::CB;
+        for (int ml = 0; ml < C::MC; ++ml) {
+            const int m = c * C::MC + ml;
+            if (m >= C::CMID) continue;                      // zero padding of the mid channels
+            for (int k = 0; k < C::CIN; ++k) put_kmajor_split(cb + C::OFF_W1H, cb + C::OFF_W1L, ml, k, C::CIN, f.w(n1)[m * C::CIN + k]);
+            cb[C::OFF_B1 + ml] = f.b(n1)[m];
+            for (int t = 0; t < 9; ++t) cb[C::OFF_WD + ml * 9 + t] = f.w(nd)[m * 9 + t];
+            cb[C::OFF_BD + ml] = f.b(nd)[m];
+            for (int n = 0; n < C::COUT; ++n) put_kmajor_split(cb + C::OFF_W2H, cb + C::OFF_W2L, n, ml, C::MC, f.w(n2)[n * C::CMID + m]);
+        }
+    }
+    for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
     return off;
 }
 
@@ -430,6 +491,16 @@ int64_t pack_upcat(std::vector<float>& out, const Folded& f) {
 }
 
 template <class C>
+Group make_irbtc(const char* name, int out_ch) {
+    Group g{};
+    g.name = name;
+    g.launch = &launch_irbtc<C>;
+    g.occupancy = &occ_irbtc<C>;
+    g.out_ch = out_ch;
+    return g;
+}
+
+template <class C>
 Group make_irb(const char* name, int out_ch) {
     Group g{};
     g.name = name;
@@ -498,6 +569,8 @@ static int alloc_all(yf_ctx* ctx) {
 
 static int ensure_out(yf_ctx* ctx, int max_det) {
     if (max_det <= ctx->out_cap) return YF_OK;
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);      // graphs bake the output pointer in
+    ctx->graphs.clear();
     if (ctx->d_out) CU(cudaFree(ctx->d_out));
     ctx->d_out = nullptr;
     CU(cudaMalloc(&ctx->d_out, sizeof(yf_det) * (size_t)max_det * ctx->max_batch));
@@ -534,10 +607,17 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes3a>("res3_1", 8), 8, 8);
     chain(make_irb<CfgRes3a>("res3_2", 8), 8, 8);
     chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
+#if YF_USE_TC
+    chain(make_irbtc<CfgRes3bTc>("res3_3", 16), 8, 8);
+    chain(make_irbtc<CfgRes3bTc>("res3_4", 16), 8, 8);
+    chain(make_irbtc<CfgRes3bTc>("res3_5", 16), 8, 8);
+    chain(make_irbtc<CfgRes3bTc>("res3_6", 16), 8, 8);
+#else
     chain(make_irb<CfgRes3b>("res3_3", 16), 8, 8);
     chain(make_irb<CfgRes3b>("res3_4", 16), 8, 8);
     chain(make_irb<CfgRes3b>("res3_5", 16), 8, 8);
     chain(make_irb<CfgRes3b>("res3_6", 16), 8, 8);
+#endif
     chain(make_irb<CfgDown3>("conv4_1", 24), 8, 16);
     chain(make_irb<CfgRes4>("res4_1", 24), 16, 16);
     chain(make_irb<CfgRes4>("res4_2", 24), 16, 16);
@@ -610,7 +690,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         cudaFuncSetAttribute(pw_kernel<CfgPw52>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPw52::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
         init_irb<CfgRes1>(), init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -630,6 +710,7 @@ extern "C" void yf_destroy(yf_ctx* ctx) {
     cudaFree(ctx->d_out); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
     cudaFree(ctx->p_rec); cudaFree(ctx->p_conf); cudaFree(ctx->p_cls); cudaFree(ctx->p_sbox); cudaFree(ctx->p_order);
     cudaFree(ctx->p_alive); cudaFree(ctx->n_alive);
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);
     if (ctx->s_copy) {
         cudaStreamSynchronize(ctx->s_copy); cudaStreamSynchronize(ctx->s_comp);
         for (int i = 0; i < 2; ++i) {
@@ -665,7 +746,12 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     offs.push_back(pack_irb<CfgDown2>(P, f, "conv2_2", "conv2_3", "conv3_1", "", 0));
     res(CfgRes3a{}, "res3_1"); res(CfgRes3a{}, "res3_2");
     offs.push_back(pack_irb<CfgWide3>(P, f, "conv3_2", "conv3_3", "conv3_4", "", 0));
+#if YF_USE_TC
+    for (const char* n : {"res3_3", "res3_4", "res3_5", "res3_6"})
+        offs.push_back(pack_irbtc<CfgRes3bTc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
+#else
     res(CfgRes3b{}, "res3_3"); res(CfgRes3b{}, "res3_4"); res(CfgRes3b{}, "res3_5"); res(CfgRes3b{}, "res3_6");
+#endif
     offs.push_back(pack_irb<CfgDown3>(P, f, "conv3_5", "conv3_6", "conv4_1", "", 0));
     res(CfgRes4{}, "res4_1"); res(CfgRes4{}, "res4_2"); res(CfgRes4{}, "res4_3"); res(CfgRes4{}, "res4_4");
     offs.push_back(pack_irb<CfgDown4>(P, f, "conv4_2", "conv4_3", "conv5_1", "", 0));
@@ -678,6 +764,8 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     offs.push_back(pack_irb<CfgNeckL2>(P, f, "", "conv4_1_4", "conv4_1_5", "head_4", ctx->nout));
     pad4(P);
     if (offs.size() != ctx->groups.size()) { set_err(&ctx->err, "internal: %zu packs vs %zu groups", offs.size(), ctx->groups.size()); return YF_ERR_STATE; }
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);      // graphs bake the weight pointers in
+    ctx->graphs.clear();
     if (ctx->d_w) CU(cudaFree(ctx->d_w));
     ctx->d_w = nullptr;
     CU(cudaMalloc(&ctx->d_w, sizeof(float) * P.size()));
@@ -889,6 +977,39 @@ extern "C" int yf_detect(yf_ctx* ctx, const float* x, int B, const yf_post_param
     return detect_impl(ctx, x, false, B, p, out, counts, status, (cudaStream_t)stream);
 }
 
+// detect_impl on library-owned buffers, replayed from a CUDA graph for small batches (31 launches cost more on the
+// host than on the device at batch 1). The graph is keyed by everything baked into the kernel arguments.
+static const int kGraphMaxBatch = 16;
+static int detect_fixed(yf_ctx* ctx, const void* xdev, bool u8in, int B, const yf_post_params* p, yf_det* out, int32_t* counts,
+                        int32_t* status, cudaStream_t st) {
+    static const bool no_graph = getenv("YF_DEBUG_SYNC") != nullptr || getenv("YF_NO_GRAPH") != nullptr;
+    if (B > kGraphMaxBatch || no_graph) return detect_impl(ctx, xdev, u8in, B, p, out, counts, status, st);
+    std::string key(reinterpret_cast<const char*>(p), sizeof(*p));
+    const void* ptrs[4] = {xdev, out, counts, status};
+    key.append(reinterpret_cast<const char*>(ptrs), sizeof ptrs);
+    key.push_back((char)B); key.push_back((char)u8in);
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end()) {
+        if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const int64_t before = ctx->launches;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = detect_impl(ctx, xdev, u8in, B, p, out, counts, status, st);
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        const int n = (int)(ctx->launches - before);
+        ctx->launches = before;                              // captured, not executed
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { set_err(&ctx->err, "graph capture failed: %s", cudaGetErrorString(e)); return YF_ERR_CUDA; }
+        CU(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = ctx->graphs.emplace(key, std::make_pair(exec, n)).first;
+    }
+    CU(cudaGraphLaunch(it->second.first, st));
+    ctx->launches += it->second.second;
+    return YF_OK;
+}
+
 static int detect_host_impl(yf_ctx* ctx, const void* x_host, bool u8in, int B, const yf_post_params* p, yf_det* out_host,
                             int32_t* counts_host, int32_t* status_host, cudaStream_t st) {
     if (!x_host || !p || !out_host || !counts_host) { set_err(&ctx->err, "null argument"); return YF_ERR_ARG; }
@@ -901,7 +1022,7 @@ static int detect_host_impl(yf_ctx* ctx, const void* x_host, bool u8in, int B, c
     const void* xdev;
     if (u8in) { CU(cudaMemcpyAsync(ctx->d_u8, x_host, npx, cudaMemcpyHostToDevice, st)); xdev = ctx->d_u8; }
     else { CU(cudaMemcpyAsync(ctx->d_x, x_host, npx * sizeof(float), cudaMemcpyHostToDevice, st)); xdev = ctx->d_x; }
-    rc = detect_impl(ctx, xdev, u8in, B, p, ctx->d_out, ctx->d_counts, ctx->d_status, st);
+    rc = detect_fixed(ctx, xdev, u8in, B, p, ctx->d_out, ctx->d_counts, ctx->d_status, st);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out_host, ctx->d_out, sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(counts_host, ctx->d_counts, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
@@ -964,6 +1085,8 @@ static int submit_impl(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, con
     if (rc) return rc;
     if (p->max_det > ctx->sl_out_cap[slot]) {
         if (ctx->sl_used[slot]) CU(cudaEventSynchronize(ctx->sl_done[slot]));
+        for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);
+        ctx->graphs.clear();
         if (ctx->sl_out[slot]) CU(cudaFree(ctx->sl_out[slot]));
         ctx->sl_out[slot] = nullptr;
         CU(cudaMalloc(&ctx->sl_out[slot], sizeof(yf_det) * (size_t)p->max_det * ctx->max_batch));
@@ -979,7 +1102,7 @@ static int submit_impl(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, con
         if (rc) return rc;
         CU(cudaEventRecord(ctx->sl_free[slot], ctx->s_comp));
     } else {
-        rc = detect_impl(ctx, ctx->sl_u8[slot], true, B, p, ctx->sl_out[slot], ctx->sl_counts[slot], ctx->sl_status[slot], ctx->s_comp);
+        rc = detect_fixed(ctx, ctx->sl_u8[slot], true, B, p, ctx->sl_out[slot], ctx->sl_counts[slot], ctx->sl_status[slot], ctx->s_comp);
         if (rc) return rc;
         CU(cudaEventRecord(ctx->sl_free[slot], ctx->s_comp));
         CU(cudaMemcpyAsync(out_host, ctx->sl_out[slot], sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, ctx->s_comp));
