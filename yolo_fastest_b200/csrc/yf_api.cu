@@ -148,6 +148,7 @@ struct yf_ctx {
     unsigned char* p_alive = nullptr;
     // double-buffered asynchronous host path (yf_detect_submit_u8 / yf_detect_wait)
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_cap = nullptr;                       // graphs are captured here (the caller's stream may be the legacy stream, which cannot capture)
     unsigned char* sl_u8[2] = {nullptr, nullptr};
     yf_det* sl_out[2] = {nullptr, nullptr};
     int sl_out_cap[2] = {0, 0};
@@ -210,9 +211,9 @@ using CfgWide3 = YF_CFGWIDE3;
 #define YF_CFGRES3B IrbCfg<16, 96, 16, 3, 1, 8, 40, 16, 8, 8, 8, 256, 2, true, true, false, false>
 #endif
 using CfgRes3b = YF_CFGRES3B;
-// tensor-core (tcgen05, 3xTF32) variant for the wide residual blocks: IrbTcCfg<CIN, CMID, COUT, TH, TW, MC, RH, NT, RES>
+// tensor-core (tcgen05, 3xTF32) variant for the wide residual blocks: IrbTcCfg<CIN, CMID, COUT, TH, TW, MC, RH, worker warps, RES>
 #ifndef YF_CFGRES3B_TC
-#define YF_CFGRES3B_TC IrbTcCfg<16, 96, 16, 8, 40, 16, 8, 256, true>
+#define YF_CFGRES3B_TC IrbTcCfg<16, 96, 16, 8, 40, 32, 8, 10, true>
 #endif
 using CfgRes3bTc = YF_CFGRES3B_TC;
 #ifndef YF_USE_TC
@@ -401,7 +402,9 @@ int64_t pack_irbtc(std::vector<float>& out, const Folded& f, const std::string& 
             cb[C::OFF_B1 + ml] = f.b(n1)[m];
             for (int t = 0; t < 9; ++t) cb[C::OFF_WD + ml * 9 + t] = f.w(nd)[m * 9 + t];
             cb[C::OFF_BD + ml] = f.b(nd)[m];
-            for (int n = 0; n < C::COUT; ++n) put_kmajor_split(cb + C::OFF_W2H, cb + C::OFF_W2L, n, ml, C::MC, f.w(n2)[n * C::CMID + m]);
+            // project weights as one B operand of 2*COUTP rows: rows [0, COUTP) = hi parts, rows [COUTP, 2*COUTP) = lo parts
+            for (int n = 0; n < C::COUT; ++n)
+                put_kmajor_split(cb + C::OFF_W2, cb + C::OFF_W2 + C::COUTP * C::MC, n, ml, C::MC, f.w(n2)[n * C::CMID + m]);
         }
     }
     for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
@@ -711,6 +714,7 @@ extern "C" void yf_destroy(yf_ctx* ctx) {
     cudaFree(ctx->p_rec); cudaFree(ctx->p_conf); cudaFree(ctx->p_cls); cudaFree(ctx->p_sbox); cudaFree(ctx->p_order);
     cudaFree(ctx->p_alive); cudaFree(ctx->n_alive);
     for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);
+    if (ctx->s_cap) cudaStreamDestroy(ctx->s_cap);
     if (ctx->s_copy) {
         cudaStreamSynchronize(ctx->s_copy); cudaStreamSynchronize(ctx->s_comp);
         for (int i = 0; i < 2; ++i) {
@@ -994,9 +998,10 @@ static int detect_fixed(yf_ctx* ctx, const void* xdev, bool u8in, int B, const y
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         const int64_t before = ctx->launches;
-        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = detect_impl(ctx, xdev, u8in, B, p, out, counts, status, st);
-        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (!ctx->s_cap) CU(cudaStreamCreateWithFlags(&ctx->s_cap, cudaStreamNonBlocking));
+        CU(cudaStreamBeginCapture(ctx->s_cap, cudaStreamCaptureModeThreadLocal));
+        int rc = detect_impl(ctx, xdev, u8in, B, p, out, counts, status, ctx->s_cap);
+        cudaError_t e = cudaStreamEndCapture(ctx->s_cap, &graph);
         const int n = (int)(ctx->launches - before);
         ctx->launches = before;                              // captured, not executed
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }

@@ -1,5 +1,5 @@
-// yf_tc.cuh — tensor-core (tcgen05) variant of the inverted-residual engine for the wide blocks, where the two
-// 1x1 convolutions are real dense contractions (K = 16..48 in, N = 96..224 mid, yolo_fastest.py:52-66).
+// yf_tc.cuh — tensor-core (tcgen05) inverted-residual engine for the wide blocks, where the two 1x1 convolutions
+// are real dense contractions (K = 16..48 in, N = 96..224 mid, yolo_fastest.py:52-66).
 //
 //   S1  E[halo px][MC]  = X[halo px][CIN] . W1[CIN][MC]      tcgen05.mma kind::tf32, M = 128 pixels per MMA tile
 //   dw  D = relu(dw3x3(relu(E + b1)) + bd)                     CUDA cores, sliding window (as in yf_kernels.cuh)
@@ -9,21 +9,31 @@
 // product is issued as hi*hi + hi*lo + lo*hi (fp32 accumulation in TMEM); measured error 8e-7 relative
 // (tools/selftest/umma_selftest.cu), i.e. fp32 grade, where a single TF32 pass would give 1e-3.
 //
+// Warp-specialised, one CTA per SM: NWW worker warps run the CUDA-core phases of a chunk of MC mid channels
+// (TMEM -> bias/ReLU/mask -> E in smem; depthwise -> D as MMA operand), one extra warp owns the tensor core: a single
+// thread issues every tcgen05.mma and every weight-block bulk copy and talks to the workers through mbarriers only.
+// The stream of chunks s = 0, 1, ... (all tiles of this persistent CTA back to back) is software pipelined:
+//   expand MMA of chunk s+1 runs during the depthwise phase of chunk s     (trigger: e1free, TMEM E read out)
+//   project MMA of chunk s  runs during the TMEM read-out of chunk s+1     (trigger: dfull, operand D written)
+//   weight block of chunk s+2 is in flight (3-deep ring), the next tile's input is fetched to registers one phase ahead.
+//
 // Operand layouts (validated by the selftest):
 //   A = activations, MN-major (pixels contiguous) — for 32-bit MN-major operands the only legal shared-memory layout
 //       is SWIZZLE_128B_BASE32B: atoms of [4 channels][32 pixels] fp32 = 512 B, the 32-byte chunk index XOR-ed with
 //       (channel & 3); two atoms per MMA (K = 8), LBO = stride between 32-pixel atoms, SBO = stride between 4-channel atoms.
 //   B = weights, K-major, no swizzle, packed on the host as [n/8][k/4][n%8][k%4] (core matrices of 8 rows x 16 bytes).
+//       The project weights are packed as [W2hi ; W2lo] along N, so D_hi . [W2hi | W2lo] is ONE pass over the operand D
+//       (N = 2*COUTP) and D_lo . W2hi the second; the output epilogue adds the two column groups.
 //   D = TMEM, lane = pixel, column = output channel; the epilogues read it with tcgen05.ld.32x32b (thread = pixel).
 #pragma once
 #include "yf_kernels.cuh"
 
 namespace yf {
 
+// hi part of the 3xTF32 split: round to nearest (ties away) at 10 mantissa bits, as cvt.rna.tf32.f32 does for finite
+// values; written as integer add + mask (2 instructions — the cvt expands to 4 with its inf/nan guard)
 __device__ __forceinline__ float tf32_hi(float v) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 // float index of activation element (pixel m, channel k) in an A operand region; kblk = floats per 8-channel block
 __device__ __forceinline__ int a_idx(int m, int k, int kblk) {
@@ -47,6 +57,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int ID, int N>
+__device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -60,40 +76,49 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 constexpr int pow2_ge(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
-template <int CIN_, int CMID_, int COUT_, int TH_, int TW_, int MC_, int RH_, int NT_, bool RES_>
+template <int CIN_, int CMID_, int COUT_, int TH_, int TW_, int MC_, int RH_, int NWW_, bool RES_>
 struct IrbTcCfg {
-    static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_, MC = MC_, RH = RH_, NT = NT_;
+    static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_, MC = MC_, RH = RH_, NWW = NWW_;
+    static constexpr int NTW = NWW * 32;          // worker threads
+    static constexpr int NT = NTW + 32;           // + the tensor-core warp
+    static constexpr int NWB = 3;                 // weight-block ring
     static constexpr bool RES = RES_;
     using G = Geo<3, 1, TH_, TW_>;
     static constexpr int CMIDP = rup(CMID, MC), NCHUNK = CMIDP / MC;
     static constexpr int MT1 = cdiv(G::IPIX, 128), MT3 = cdiv(G::OPIX, 128);      // 128-pixel MMA tiles of the halo / output tile
-    static constexpr int NP3 = rup(COUT, 16);                                     // N of the project MMA (M = 128 needs N % 16 == 0)
-    static constexpr int KB1 = MT1 * 1024, KB3 = MT3 * 1024;                      // floats per 8-channel block of an A region
+    static constexpr int NG1 = cdiv(G::IPIX, 32), NG3 = cdiv(G::OPIX, 32);        // 32-pixel operand atoms actually stored
+    static constexpr int COUTP = rup(COUT, 16);                                   // N of the lo pass (M = 128 needs N % 16 == 0)
+    static constexpr int KB1 = NG1 * 256, KB3 = NG3 * 256;                        // floats per 8-channel block of an A region
     static constexpr int XA1 = (CIN / 8) * KB1, DA1 = (MC / 8) * KB3;             // floats of one A region (hi or lo)
     static constexpr int TM_E = 0, TM_O = MT1 * MC;                               // TMEM columns: expand accumulators, project accumulators
-    static constexpr int TCOLS = pow2_ge(TM_O + MT3 * NP3);
+    static constexpr int TCOLS = pow2_ge(TM_O + MT3 * 2 * COUTP);
     // weight block of one chunk (floats)
-    static constexpr int OFF_W1H = 0, OFF_W1L = MC * CIN, OFF_B1 = 2 * MC * CIN, OFF_WD = OFF_B1 + MC, OFF_BD = OFF_WD + MC * 9;
-    static constexpr int OFF_W2H = OFF_BD + MC, OFF_W2L = OFF_W2H + NP3 * MC, CB = OFF_W2L + NP3 * MC;
+    static constexpr int OFF_W1H = 0, OFF_W1L = MC * CIN, OFF_W2 = 2 * MC * CIN, OFF_B1 = OFF_W2 + 2 * COUTP * MC;
+    static constexpr int OFF_WD = OFF_B1 + MC, OFF_BD = OFF_WD + MC * 9, CB = rup(OFF_BD + MC, 32);
     static constexpr int OFF_B2 = NCHUNK * CB;
     static constexpr int WFLOATS = OFF_B2 + COUT;
-    static constexpr int XRAW = rup(CIN * G::IPIX, 32), ES = rup(MC * G::IPIX, 32), WS1 = rup(CB, 32);
-    static constexpr int SMEM_FLOATS = 2 * XA1 + 2 * DA1 + XRAW + ES + 2 * WS1;
+    static constexpr int ES = rup(MC * G::IPIX, 32);
+    static constexpr int SMEM_FLOATS = 2 * XA1 + 2 * DA1 + ES + NWB * CB;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + 1024;     // + slack to align the dynamic window to 1 KB
-    static_assert(CIN % 8 == 0 && MC % 16 == 0 && NT % 128 == 0 && CB % 4 == 0, "tcgen05 tiling constraints");
+    static constexpr int NITEM_X = (CIN / 8) * G::IPIX;           // input staging items (8 channels of one halo pixel) per tile
+    static constexpr int NIT = cdiv(NITEM_X, NTW);                // ... per worker thread
+    static_assert(CIN % 8 == 0 && MC % 32 == 0 && NWW >= 4, "tcgen05 tiling constraints");
     static_assert(TCOLS <= 512, "TMEM columns");
     static_assert(!RES || CIN == COUT, "residual needs same shape");
     static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
+    // the last MMA tile of an operand region reads up to 3 atoms past the stored ones (results land in unused TMEM lanes);
+    // those reads must stay inside the dynamic window: something at least 3 KB long follows every region
+    static_assert(ES * 4 >= 4096, "over-read guard");
 };
 
 // depthwise 3x3 s1 + bias + ReLU from E [MC][halo] into the A-operand layout of the project MMA (hi and lo parts)
 template <class G, int MC, int RH, int NT, int KB3>
-__device__ __forceinline__ void dw_stage_split(const float* __restrict__ Es, const float* __restrict__ Wd, const float* __restrict__ bd,
+__device__ __forceinline__ void dw_stage_split(int tid, const float* __restrict__ Es, const float* __restrict__ Wd, const float* __restrict__ bd,
                                                float* __restrict__ DAhi, float* __restrict__ DAlo) {
     static_assert(G::TH % RH == 0 && G::S == 1 && G::KS == 3, "3x3 stride 1");
     constexpr int NSTRIP = G::TW / 4, NSEG = G::TH / RH;
     constexpr int NITEM = MC * NSEG * NSTRIP;
-    for (int item = threadIdx.x; item < NITEM; item += NT) {
+    for (int item = tid; item < NITEM; item += NT) {
         const int m = item / (NSEG * NSTRIP);
         const int rem = item - m * (NSEG * NSTRIP);
         const int seg = rem / NSTRIP;
@@ -140,178 +165,250 @@ __global__ void __launch_bounds__(C::NT, 1)
 irbtc_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts, int H, int W,
              int tiles_x, int tiles_y, int total_tiles) {
     using G = typename C::G;
-    constexpr int NT = C::NT, NW = NT / 32;
+    constexpr int NTW = C::NTW, NWW = C::NWW;
     extern __shared__ unsigned char smem_raw[];
-    float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // align the dynamic window to 1 KB by OFFSET, so the pointers keep their shared-memory provenance (LDS/STS, not generic LD/ST)
+    float* base = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     float* XAhi = base;
     float* XAlo = XAhi + C::XA1;
     float* DAhi = XAlo + C::XA1;
     float* DAlo = DAhi + C::DA1;
-    float* Xraw = DAlo + C::DA1;
-    float* Es = Xraw + C::XRAW;
+    float* Es = DAlo + C::DA1;
     float* Ws = Es + C::ES;
-    __shared__ __align__(8) uint64_t wbar[2], mbar1, mbar3;
+    __shared__ __align__(8) uint64_t wbar[C::NWB], xfull, e1full, e1free, dfull, dfree;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quarter = warp & 3, wgrp = warp >> 2;     // TMEM lane quarter this warp may access; warps sharing a quarter split the MMA tiles
-    constexpr int NGRP = NW / 4;
-
-    auto origin = [&](int tile, int& b, int& oy0, int& ox0) {
-        const int tx = tile % tiles_x;
-        const int r = tile / tiles_x;
-        oy0 = (r % tiles_y) * G::TH; ox0 = tx * G::TW; b = r / tiles_y;
-    };
-    auto stage_tile = [&](int tile) {
-        int b, oy0, ox0;
-        origin(tile, b, oy0, ox0);
-        load_rect_async<G::IH, G::IW, G::IWS, NT>(Xraw, x + (size_t)b * C::CIN * H * W, C::CIN, C::CIN, H, W, oy0 - 1, ox0 - 1);
-        cp_async_commit();
-    };
-    auto issue_w = [&](int chunk, int buf) {
-        mbar_expect_tx(&wbar[buf], C::CB * 4);
-        bulk_load(Ws + buf * C::WS1, wts + (size_t)chunk * C::CB, C::CB * 4, &wbar[buf]);
-    };
 
     if (tid == 0) {
-        mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_init(&mbar1, 1); mbar_init(&mbar3, 1);
+        for (int i = 0; i < C::NWB; ++i) mbar_init(&wbar[i], 1);
+        mbar_init(&xfull, NWW); mbar_init(&e1full, 1); mbar_init(&e1free, NWW); mbar_init(&dfull, NWW); mbar_init(&dfree, 1);
         mbar_fence_init();
     }
-    if (warp == 0) {
+    if (warp == NWW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)C::TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // the pad pixels (m >= IPIX / OPIX) of the operand regions are never written again: zero everything once
-    for (int i = tid * 4; i < 2 * C::XA1 + 2 * C::DA1; i += NT * 4) st4(XAhi + i, make_float4(0.f, 0.f, 0.f, 0.f));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
 
-    int tile = blockIdx.x;
-    if (tile < total_tiles) {
-        if (tid == 0) issue_w(0, 0);
-        stage_tile(tile);
-    }
-    constexpr uint32_t IDESC1 = umma_idesc_tf32(C::MC), IDESC3 = umma_idesc_tf32(C::NP3);
-    uint32_t q = 0, ph1 = 0, ph3 = 0;
-    for (; tile < total_tiles; tile += gridDim.x) {
-        int tb, oy0, ox0;
-        origin(tile, tb, oy0, ox0);
-        const int iy0 = oy0 - 1, ix0 = ox0 - 1;
-        const bool have_next = tile + (int)gridDim.x < total_tiles;
-        cp_async_wait_all();
-        __syncthreads();                       // raw tile landed; the previous tile is completely done
-        for (int idx = tid; idx < C::CIN * G::IPIX; idx += NT) {
-            const int k = idx / G::IPIX, m = idx - k * G::IPIX;
-            const float v = Xraw[idx];
-            const float hi = tf32_hi(v);
-            const int o = a_idx(m, k, C::KB1);
-            XAhi[o] = hi;
-            XAlo[o] = v - hi;
-        }
-        fence_proxy_async();
-        __syncthreads();                       // operand A of the expand MMA is visible to the tensor core; Xraw is free
-        if (have_next) stage_tile(tile + gridDim.x);
+    const int ntile = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int S = ntile * C::NCHUNK;                     // chunk steps of this CTA
 
-        for (int c = 0; c < C::NCHUNK; ++c, ++q) {
-            const int wbuf = (int)(q & 1);
-            const float* Wc = Ws + wbuf * C::WS1;
-            mbar_wait(&wbar[wbuf], (q >> 1) & 1);
-            // ---- S1: expand on the tensor core ---------------------------------------------------------------
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t w1h = smem_u32(Wc + C::OFF_W1H), w1l = smem_u32(Wc + C::OFF_W1L);
-                const uint32_t xh = smem_u32(XAhi), xl = smem_u32(XAlo);
+    if (warp == NWW) {
+        // ================= tensor-core warp: one thread issues every MMA and every weight copy =================
+        if (lane == 0 && S > 0) {
+            constexpr uint32_t IDESC1 = umma_idesc_tf32(C::MC), IDESC3A = umma_idesc_tf32(2 * C::COUTP), IDESC3B = umma_idesc_tf32(C::COUTP);
+            const uint32_t xh = smem_u32(XAhi), xl = smem_u32(XAlo), dh = smem_u32(DAhi), dl = smem_u32(DAlo), ws = smem_u32(Ws);
+            auto issue_w = [&](int s) {
+                const int buf = s % C::NWB;
+                mbar_expect_tx(&wbar[buf], C::CB * 4);
+                bulk_load(Ws + buf * C::CB, wts + (size_t)(s % C::NCHUNK) * C::CB, C::CB * 4, &wbar[buf]);
+            };
+            // descriptor bases; an MMA adds its byte offset >> 4 to the 14-bit start-address field (never carries: smem < 256 KB)
+            const uint64_t dxh = umma_desc(xh, 1024, 512, 1), dxl = umma_desc(xl, 1024, 512, 1);
+            const uint64_t ddh = umma_desc(dh, 1024, 512, 1), ddl = umma_desc(dl, 1024, 512, 1);
+            const uint64_t dw1 = umma_desc(ws, 128, (C::CIN / 4) * 128, 0), dw2 = umma_desc(ws + C::OFF_W2 * 4, 128, (C::MC / 4) * 128, 0);
+            auto mma1 = [&](int s) {                     // expand MMA of step s into the (single) TMEM E buffer
+                const uint64_t wb = dw1 + (uint64_t)(((uint32_t)(s % C::NWB) * C::CB * 4) >> 4);
 #pragma unroll 1
                 for (int mt = 0; mt < C::MT1; ++mt) {
+                    const uint64_t mo = (uint64_t)(mt * 256);
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a0 = (pass == 2 ? xl : xh) + mt * 4096;
-                        const uint32_t b0 = (pass == 1 ? w1l : w1h);
 #pragma unroll
                         for (int kb = 0; kb < C::CIN / 8; ++kb)
-                            umma_tf32(tmem + C::TM_E + mt * C::MC, umma_desc(a0 + kb * C::KB1 * 4, 1024, 512, 1),
-                                      umma_desc(b0 + kb * 256, 128, (C::CIN / 4) * 128, 0), IDESC1, (pass | kb) ? 1u : 0u);
+                            umma_tf32(tmem + C::TM_E + mt * C::MC, (pass == 2 ? dxl : dxh) + mo + (uint64_t)(kb * C::KB1 * 4 / 16),
+                                      wb + (uint64_t)(((pass == 1 ? C::OFF_W1L : C::OFF_W1H) * 4 + kb * 256) / 16), IDESC1, (pass | kb) ? 1u : 0u);
                     }
                 }
-                umma_commit(&mbar1);
-            }
-            mbar_wait(&mbar1, ph1); ph1 ^= 1;
-            tc_fence_after();
-            // ---- S1 epilogue: TMEM -> bias + ReLU + zero outside the image -> E[ch][halo pixel] ------------------
-            for (int mt = wgrp; mt < C::MT1; mt += NGRP) {
-                const int pix = mt * 128 + quarter * 32 + lane;
-                const int r = pix / G::IWS, j = pix - r * G::IWS;
-                const bool ok = pix < G::IPIX && j < G::IW && (unsigned)(iy0 + r) < (unsigned)H && (unsigned)(ix0 + j) < (unsigned)W;
-#pragma unroll
-                for (int c0 = 0; c0 < C::MC; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(tmem + lane_base + C::TM_E + mt * C::MC + c0, v);
-                    if (pix < G::IPIX) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) Es[(c0 + i) * G::IPIX + pix] = ok ? fmaxf(v[i] + Wc[C::OFF_B1 + c0 + i], 0.f) : 0.f;
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncthreads();                   // E complete; the expand accumulators may be overwritten by the next chunk
-            if (c > 0) { mbar_wait(&mbar3, ph3); ph3 ^= 1; }      // project MMA of the previous chunk has consumed D and its weights
-            if (tid == 0 && (c + 1 < C::NCHUNK || have_next)) issue_w(c + 1 < C::NCHUNK ? c + 1 : 0, (int)((q + 1) & 1));
-            // ---- depthwise on CUDA cores, output split into the project MMA's operand ------------------------------
-            dw_stage_split<G, C::MC, C::RH, NT, C::KB3>(Es, Wc + C::OFF_WD, Wc + C::OFF_BD, DAhi, DAlo);
-            fence_proxy_async();
-            __syncthreads();                   // D complete and visible to the tensor core
-            // ---- S3: project, accumulating over the chunks in TMEM -------------------------------------------------
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t w2h = smem_u32(Wc + C::OFF_W2H), w2l = smem_u32(Wc + C::OFF_W2L);
-                const uint32_t dh = smem_u32(DAhi), dl = smem_u32(DAlo);
+                umma_commit(&e1full);
+            };
+            auto mma2 = [&](int s) {                     // project MMA of step s, accumulating over the chunks of a tile
+                const uint64_t wb = dw2 + (uint64_t)(((uint32_t)(s % C::NWB) * C::CB * 4) >> 4);
+                const uint32_t first = (s % C::NCHUNK) == 0 ? 0u : 1u;
 #pragma unroll 1
                 for (int mt = 0; mt < C::MT3; ++mt) {
+                    const uint64_t mo = (uint64_t)(mt * 256);
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a0 = (pass == 2 ? dl : dh) + mt * 4096;
-                        const uint32_t b0 = (pass == 1 ? w2l : w2h);
+                    for (int kb = 0; kb < C::MC / 8; ++kb)
+                        umma_tf32(tmem + C::TM_O + mt * 2 * C::COUTP, ddh + mo + (uint64_t)(kb * C::KB3 * 4 / 16), wb + (uint64_t)(kb * 16), IDESC3A, kb ? 1u : first);
 #pragma unroll
-                        for (int kb = 0; kb < C::MC / 8; ++kb)
-                            umma_tf32(tmem + C::TM_O + mt * C::NP3, umma_desc(a0 + kb * C::KB3 * 4, 1024, 512, 1),
-                                      umma_desc(b0 + kb * 256, 128, (C::MC / 4) * 128, 0), IDESC3, (c | pass | kb) ? 1u : 0u);
-                    }
+                    for (int kb = 0; kb < C::MC / 8; ++kb)
+                        umma_tf32(tmem + C::TM_O + mt * 2 * C::COUTP, ddl + mo + (uint64_t)(kb * C::KB3 * 4 / 16), wb + (uint64_t)(kb * 16), IDESC3B, 1u);
                 }
-                umma_commit(&mbar3);
+                umma_commit(&dfree);
+            };
+            issue_w(0);
+            if (S > 1) issue_w(1);
+            mbar_wait(&xfull, 0);
+            mbar_wait(&wbar[0], 0);
+            tc_fence_after();
+            mma1(0);
+            for (int s = 0; s < S; ++s) {
+                if (s + 1 < S) {
+                    mbar_wait(&e1free, s & 1);                                   // TMEM E of step s has been read out
+                    if ((s + 1) % C::NCHUNK == 0) mbar_wait(&xfull, ((s + 1) / C::NCHUNK) & 1);
+                    mbar_wait(&wbar[(s + 1) % C::NWB], ((s + 1) / C::NWB) & 1);
+                    tc_fence_after();
+                    mma1(s + 1);
+                }
+                if (s + 2 < S) {
+                    if (s >= 1) mbar_wait(&dfree, (s - 1) & 1);                  // ring slot (s+2)%3 == (s-1)%3: its project MMA is complete
+                    issue_w(s + 2);
+                }
+                mbar_wait(&dfull, s & 1);                                        // operand D of step s is written
+                tc_fence_after();
+                mma2(s);
             }
         }
-        mbar_wait(&mbar3, ph3); ph3 ^= 1;
-        tc_fence_after();
-        // ---- output epilogue: TMEM -> + bias (+ residual, yolo_fastest.py:65) -> HBM -------------------------------------
-        for (int mt = wgrp; mt < C::MT3; mt += NGRP) {
-            const int pix = mt * 128 + quarter * 32 + lane;
-            const int oy = pix / G::TW, ox = pix - oy * G::TW;
-            const int gy = oy0 + oy, gx = ox0 + ox;
-            const bool ok = pix < G::OPIX && gy < H && gx < W;
+    } else {
+        // ================= worker warps: CUDA-core phases ==========================================================
+        const int quarter = warp & 3, wq = warp >> 2;        // TMEM lane quarter this warp may access; rank among the warps sharing it
+        const int nwq = (NWW - quarter + 3) >> 2;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        auto origin = [&](int ti, int& b, int& oy0, int& ox0) {
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int tx = tile % tiles_x;
+            const int r = tile / tiles_x;
+            oy0 = (r % tiles_y) * G::TH; ox0 = tx * G::TW; b = r / tiles_y;
+        };
+        float xr[C::NIT * 8];
+        // input staging item = (8-channel block kh, halo pixel m): item = tid + i * NTW = kh * IPIX + m; 8 channels per item
+        auto fetch_x = [&](int ti) {                           // raw input halo tile -> registers (zero outside the image)
+            int b, oy0, ox0;
+            origin(ti, b, oy0, ox0);
+            const float* xb = x + (size_t)b * C::CIN * H * W;
+            const size_t plane = (size_t)H * W;
 #pragma unroll
-            for (int c0 = 0; c0 < C::COUT; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem + lane_base + C::TM_O + mt * C::NP3 + c0, v);
-                if (ok) {
+            for (int i = 0; i < C::NIT; ++i) {
+                const int item = tid + i * NTW;
+                const int kh = item / G::IPIX, m = item - kh * G::IPIX;
+                const int r = m / G::IWS, j = m - r * G::IWS;
+                const int gy = oy0 - 1 + r, gx = ox0 - 1 + j;
+                const bool ok = item < C::NITEM_X && j < G::IW && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+                const float* px = xb + (size_t)(kh * 8) * plane + (ok ? gy * W + gx : 0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (c0 + i < C::COUT) {
-                            const size_t o = (((size_t)tb * C::COUT + c0 + i) * H + gy) * W + gx;
-                            float r = v[i] + __ldg(wts + C::OFF_B2 + c0 + i);
-                            if (C::RES) r += __ldg(x + o);
-                            y[o] = r;
+                for (int kk = 0; kk < 8; ++kk) xr[i * 8 + kk] = ok ? __ldg(px + kk * plane) : 0.f;
+            }
+        };
+        auto put_x = [&]() {                                   // registers -> split operand A of the expand MMA
+#pragma unroll
+            for (int i = 0; i < C::NIT; ++i) {
+                const int item = tid + i * NTW;
+                if (item < C::NITEM_X) {
+                    const int kh = item / G::IPIX, m = item - kh * G::IPIX;
+                    const int ob = kh * C::KB1 + (m >> 5) * 256 + (m & 7), mc = (m & 31) >> 3;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const float v = xr[i * 8 + kk];
+                        const float hi = tf32_hi(v);
+                        const int o = ob + ((kk >> 2) & 1) * 128 + (kk & 3) * 32 + ((mc ^ (kk & 3)) << 3);
+                        XAhi[o] = hi;
+                        XAlo[o] = v - hi;
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xfull);
+        };
+        auto epilogue_out = [&](int ti) {                      // TMEM O -> + bias (+ residual, yolo_fastest.py:65) -> HBM
+            int tb, oy0, ox0;
+            origin(ti, tb, oy0, ox0);
+            for (int mt = wq; mt < C::MT3; mt += nwq) {
+                const int pix = mt * 128 + quarter * 32 + lane;
+                const int oy = pix / G::TW, ox = pix - oy * G::TW;
+                const int gy = oy0 + oy, gx = ox0 + ox;
+                const bool ok = pix < G::OPIX && gy < H && gx < W;
+#pragma unroll
+                for (int c0 = 0; c0 < C::COUT; c0 += 16) {
+                    float vh[16], vl[16];
+                    tmem_ld16(tmem + lane_base + C::TM_O + mt * 2 * C::COUTP + c0, vh);
+                    tmem_ld16(tmem + lane_base + C::TM_O + mt * 2 * C::COUTP + C::COUTP + c0, vl);
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (c0 + i < C::COUT) {
+                                const size_t o = (((size_t)tb * C::COUT + c0 + i) * H + gy) * W + gx;
+                                float r = (vh[i] + vl[i]) + __ldg(wts + C::OFF_B2 + c0 + i);
+                                if (C::RES) r += __ldg(x + o);
+                                y[o] = r;
+                            }
                         }
                     }
                 }
             }
+        };
+
+        if (ntile > 0) {
+            fetch_x(0);
+            put_x();
         }
-        tc_fence_before();
-        __syncthreads();
+        int s = 0;
+        for (int ti = 0; ti < ntile; ++ti) {
+            int tb, oy0, ox0;
+            origin(ti, tb, oy0, ox0);
+            const int iy0 = oy0 - 1, ix0 = ox0 - 1;
+            const bool have_next = ti + 1 < ntile;
+            for (int c = 0; c < C::NCHUNK; ++c, ++s) {
+                const float* Wc = Ws + (s % C::NWB) * C::CB;
+                const bool stage_next = (c == C::NCHUNK - 1) && have_next;
+                if (stage_next) fetch_x(ti + 1);               // lands during the TMEM read-out below
+                mbar_wait(&wbar[s % C::NWB], (s / C::NWB) & 1);
+                mbar_wait(&e1full, s & 1);
+                tc_fence_after();
+                // ---- TMEM -> bias + ReLU + zero outside the image -> E[ch][halo pixel] ----------------------------
+                for (int u = wq; u < C::MT1 * (C::MC / 16); u += nwq) {
+                    const int mt = u / (C::MC / 16), c0 = (u - mt * (C::MC / 16)) * 16;
+                    if (mt * 128 + quarter * 32 >= G::IPIX) break;      // warp-uniform: this warp's 32 pixels do not exist
+                    const int pix = mt * 128 + quarter * 32 + lane;
+                    const int r = pix / G::IWS, j = pix - r * G::IWS;
+                    const bool ok = j < G::IW && (unsigned)(iy0 + r) < (unsigned)H && (unsigned)(ix0 + j) < (unsigned)W;
+                    float bb[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b4 = ld4(Wc + C::OFF_B1 + c0 + 4 * i);
+                        bb[4 * i] = b4.x; bb[4 * i + 1] = b4.y; bb[4 * i + 2] = b4.z; bb[4 * i + 3] = b4.w;
+                    }
+                    float v[16];
+                    tmem_ld16(tmem + lane_base + C::TM_E + mt * C::MC + c0, v);
+                    float* ep = Es + c0 * G::IPIX + pix;
+                    const float keep = ok ? 0.f : -INFINITY;          // relu(v + b - inf) = 0 outside the image
+                    if (pix < G::IPIX) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) ep[i * G::IPIX] = fmaxf(v[i] + (bb[i] + keep), 0.f);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&e1free);
+                if (s > 0) mbar_wait(&dfree, (s - 1) & 1);     // project MMA of step s-1 complete: D is free, O of a finished tile is final
+                if (c == 0 && ti > 0) {
+                    tc_fence_after();
+                    epilogue_out(ti - 1);
+                    tc_fence_before();
+                }
+                named_bar_sync<1, NTW>();                      // E complete
+                if (stage_next) put_x();                       // every expand MMA of this tile is complete (e1full of its last chunk)
+                // ---- depthwise on CUDA cores, output split into the project MMA's operand --------------------------
+                dw_stage_split<G, C::MC, C::RH, NTW, C::KB3>(tid, Es, Wc + C::OFF_WD, Wc + C::OFF_BD, DAhi, DAlo);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&dfull);
+                named_bar_sync<2, NTW>();                      // E free
+            }
+        }
+        if (ntile > 0) {
+            mbar_wait(&dfree, (S - 1) & 1);
+            tc_fence_after();
+            epilogue_out(ntile - 1);
+            tc_fence_before();
+        }
     }
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TCOLS) : "memory");
+    if (warp == NWW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TCOLS) : "memory");
 }
 
 }  // namespace yf
