@@ -144,17 +144,19 @@ def test_zero_and_extreme_inputs(gold):
         _close(hs, rs, "constant %.3f" % fill)
 
 
-def test_tensor_core_variant():
-    """libyf_b200_tc.so = the same library with res3_3..6 on the tcgen05 kernel (3xTF32, accumulators in TMEM):
-    every tapped activation and both heads must stay within 1e-4 of the oracle (tools/check_forward.py exits 0)."""
+def test_ffma_variant():
+    """libyf_b200_ffma.so = the same library with every group on the FFMA engine (no tcgen05): both libraries must keep every
+    tapped activation and both heads within 1e-4 of the oracle (tools/check_forward.py exits 0). The default library runs
+    res3_3..6 and res4_1..4 on the tensor cores (3xTF32, accumulators in TMEM)."""
     import os
     import subprocess
     import sys
     from conftest import ROOT
-    lib = os.path.join(ROOT, "yolo_fastest_b200", "libyf_b200_tc.so")
-    assert os.path.exists(lib), "build() did not produce the tensor-core variant"
-    for res in ("512x640", "256x320"):
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_forward.py"), res, "3"],
-                           env=dict(os.environ, YF_B200_LIB=lib), capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-        assert "res3_4" in r.stdout
+    for name in ("libyf_b200.so", "libyf_b200_ffma.so"):
+        lib = os.path.join(ROOT, "yolo_fastest_b200", name)
+        assert os.path.exists(lib), "build() did not produce %s" % name
+        for res in ("512x640", "256x320"):
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_forward.py"), res, "3"],
+                               env=dict(os.environ, YF_B200_LIB=lib), capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, name + "\n" + r.stdout[-3000:] + r.stderr[-2000:]
+            assert "res3_4" in r.stdout and "res4_2" in r.stdout

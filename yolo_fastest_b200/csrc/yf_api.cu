@@ -212,12 +212,26 @@ using CfgWide3 = YF_CFGWIDE3;
 #endif
 using CfgRes3b = YF_CFGRES3B;
 // tensor-core (tcgen05, 3xTF32) variant for the wide residual blocks: IrbTcCfg<CIN, CMID, COUT, TH, TW, MC, RH, worker warps, RES>
+#ifndef YF_TC3_TH          // tile / chunk / rows-per-item / worker warps of the res3_3..6 instantiation (tools/tc_sweep.sh overrides them)
+#define YF_TC3_TH 8
+#define YF_TC3_TW 40
+#define YF_TC3_MC 32
+#define YF_TC3_RH 8
+#define YF_TC3_NWW 10
+#endif
+#ifndef YF_TC3_E1ALL
+#define YF_TC3_E1ALL false
+#endif
 #ifndef YF_CFGRES3B_TC
-#define YF_CFGRES3B_TC IrbTcCfg<16, 96, 16, 8, 40, 32, 8, 10, true>
+#define YF_CFGRES3B_TC IrbTcCfg<16, 96, 16, YF_TC3_TH, YF_TC3_TW, YF_TC3_MC, YF_TC3_RH, YF_TC3_NWW, true, YF_TC3_E1ALL>
 #endif
 using CfgRes3bTc = YF_CFGRES3B_TC;
+#ifndef YF_CFGRES4_TC
+#define YF_CFGRES4_TC IrbTcCfg<24, 136, 24, 8, 20, 32, 4, 10, true, true>
+#endif
+using CfgRes4Tc = YF_CFGRES4_TC;
 #ifndef YF_USE_TC
-#define YF_USE_TC 0     // 1: res3_3..6 run on the tcgen05 kernel (correct, not yet faster than the FFMA engine; built as libyf_b200_tc.so)
+#define YF_USE_TC 1     // 1: res3_3..6 and res4_1..4 run on the tcgen05 kernel (yf_tc.cuh); 0: everything on the FFMA engine (libyf_b200_ffma.so)
 #endif
 #ifndef YF_CFGDOWN3
 #define YF_CFGDOWN3 IrbCfg<16, 96, 24, 3, 2, 4, 40, 16, 8, 8, 4, 256, 2, true, false, false, false>
@@ -394,11 +408,15 @@ int64_t pack_irbtc(std::vector<float>& out, const Folded& f, const std::string& 
     out.resize(off + C::WFLOATS, 0.f);
     float* o = out.data() + off;
     for (int c = 0; c < C::NCHUNK; ++c) {
-        float* cb = o + (int64_t)c * C::CB;
+        float* cb = o + C::OFF_CH + (int64_t)c * C::CB;
         for (int ml = 0; ml < C::MC; ++ml) {
             const int m = c * C::MC + ml;
             if (m >= C::CMID) continue;                      // zero padding of the mid channels
-            for (int k = 0; k < C::CIN; ++k) put_kmajor_split(cb + C::OFF_W1H, cb + C::OFF_W1L, ml, k, C::CIN, f.w(n1)[m * C::CIN + k]);
+            // expand weights: one resident B operand over all mid channels (E1ALL), or one per chunk block
+            for (int k = 0; k < C::CIN; ++k) {
+                if (C::E1ALL) put_kmajor_split(o + C::OFF_W1H, o + C::OFF_W1L, m, k, C::CIN, f.w(n1)[m * C::CIN + k]);
+                else put_kmajor_split(cb + C::OFF_W1H, cb + C::OFF_W1L, ml, k, C::CIN, f.w(n1)[m * C::CIN + k]);
+            }
             cb[C::OFF_B1 + ml] = f.b(n1)[m];
             for (int t = 0; t < 9; ++t) cb[C::OFF_WD + ml * 9 + t] = f.w(nd)[m * 9 + t];
             cb[C::OFF_BD + ml] = f.b(nd)[m];
@@ -622,10 +640,17 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes3b>("res3_6", 16), 8, 8);
 #endif
     chain(make_irb<CfgDown3>("conv4_1", 24), 8, 16);
+#if YF_USE_TC
+    chain(make_irbtc<CfgRes4Tc>("res4_1", 24), 16, 16);
+    chain(make_irbtc<CfgRes4Tc>("res4_2", 24), 16, 16);
+    chain(make_irbtc<CfgRes4Tc>("res4_3", 24), 16, 16);
+    chain(make_irbtc<CfgRes4Tc>("res4_4", 24), 16, 16);
+#else
     chain(make_irb<CfgRes4>("res4_1", 24), 16, 16);
     chain(make_irb<CfgRes4>("res4_2", 24), 16, 16);
     chain(make_irb<CfgRes4>("res4_3", 24), 16, 16);
     chain(make_irb<CfgRes4>("res4_4", 24), 16, 16);
+#endif
     {
         Group g = make_irb<CfgDown4>("conv5_1", 48);
         g.a.skip = ctx->d_skip;
@@ -693,7 +718,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         cudaFuncSetAttribute(pw_kernel<CfgPw52>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPw52::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
         init_irb<CfgRes1>(), init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -757,7 +782,12 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     res(CfgRes3b{}, "res3_3"); res(CfgRes3b{}, "res3_4"); res(CfgRes3b{}, "res3_5"); res(CfgRes3b{}, "res3_6");
 #endif
     offs.push_back(pack_irb<CfgDown3>(P, f, "conv3_5", "conv3_6", "conv4_1", "", 0));
+#if YF_USE_TC
+    for (const char* n : {"res4_1", "res4_2", "res4_3", "res4_4"})
+        offs.push_back(pack_irbtc<CfgRes4Tc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
+#else
     res(CfgRes4{}, "res4_1"); res(CfgRes4{}, "res4_2"); res(CfgRes4{}, "res4_3"); res(CfgRes4{}, "res4_4");
+#endif
     offs.push_back(pack_irb<CfgDown4>(P, f, "conv4_2", "conv4_3", "conv5_1", "", 0));
     res(CfgRes5{}, "res5_1"); res(CfgRes5{}, "res5_2"); res(CfgRes5{}, "res5_3"); res(CfgRes5{}, "res5_4"); res(CfgRes5{}, "res5_5");
     offs.push_back(pack_pw52(P, f));
@@ -853,6 +883,13 @@ extern "C" int yf_profile_forward(yf_ctx* ctx, const float* x, int B, const char
     for (auto& e : ev) cudaEventDestroy(e);
     return w;
 }
+
+#ifdef YF_TC_TRACE
+// debug builds only: copy the phase trace of the last tensor-core launch (16 slots x 64 steps of clock64) to the host
+extern "C" int yf_debug_trace(long long* dst, int n) {
+    return (int)cudaMemcpyFromSymbol(dst, yf::g_tc_trace, sizeof(long long) * (size_t)(n < 16 * 64 ? n : 16 * 64));
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // post-processing
