@@ -15,6 +15,7 @@
 #include "yf_kernels.cuh"
 #include "yf_post.cuh"
 #include "yf_tc.cuh"
+#include "yf_thin.cuh"
 
 using namespace yf;
 
@@ -187,6 +188,15 @@ using CfgStem = YF_CFGSTEM;
 #define YF_CFGRES1 IrbCfg<4, 8, 4, 3, 1, 8, 80, 8, 8, 4, 8, 256, 3, true, true, false, false>
 #endif
 using CfgRes1 = YF_CFGRES1;
+// register-resident kernel for the thin block res1_1: ThinCfg<CIN, CMID, COUT, TH, TW, RH, MPAR, min blocks/SM, RES>
+#ifndef YF_CFGRES1_THIN
+#define YF_CFGRES1_THIN ThinCfg<4, 8, 4, 32, 64, 4, 1, 2, true>
+#endif
+using CfgRes1Thin = YF_CFGRES1_THIN;
+#ifndef YF_USE_THIN
+#define YF_USE_THIN 0   // measured (B200, 640x512, batch 256): 0.44 ms = no better than the generic engine's 0.45 ms; the kernel is
+#endif                  // register-bound (255 registers, 8 warps/SM) — kept as an opt-in experiment, see DESIGN.md
+
 #ifndef YF_CFGDENSE
 #define YF_CFGDENSE DenseCfg<8, 40, 4, 128, 3, 2>
 #endif
@@ -296,6 +306,17 @@ int occ_dense() { return occ_of(dense_kernel<CfgDense>, CfgDense::NT, CfgDense::
 int occ_upcat() { return occ_of(upcat_kernel<CfgUpCat>, CfgUpCat::NT, CfgUpCat::SMEM_BYTES); }
 
 template <class C>
+void launch_thin(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    thin_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+}
+template <class C> int occ_thin() { return occ_of(thin_kernel<C>, C::NT, C::SMEM_BYTES); }
+template <class C>
+cudaError_t init_thin() { return cudaFuncSetAttribute(thin_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
+
+template <class C>
 void launch_irbtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using G = typename C::G;
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
@@ -398,6 +419,24 @@ inline void put_kmajor_split(float* hi, float* lo, int n, int k, int K, float w)
     const float h = tf32_rna_host(w);
     hi[idx] = h;
     lo[idx] = w - h;
+}
+
+template <class C>
+int64_t pack_thin(std::vector<float>& out, const Folded& f, const std::string& n1, const std::string& nd, const std::string& n2) {
+    pad4(out);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int m = 0; m < C::CMID; ++m) {
+        float* wm = o + (int64_t)m * C::WM;
+        for (int k = 0; k < C::CIN; ++k) wm[C::OFF_W1 + k] = f.w(n1)[m * C::CIN + k];
+        wm[C::OFF_B1] = f.b(n1)[m];
+        for (int t = 0; t < 9; ++t) wm[C::OFF_WD + t] = f.w(nd)[m * 9 + t];
+        wm[C::OFF_BD] = f.b(nd)[m];
+        for (int n = 0; n < C::COUT; ++n) wm[C::OFF_W2 + n] = f.w(n2)[n * C::CMID + m];
+    }
+    for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
+    return off;
 }
 
 template <class C>
@@ -512,6 +551,16 @@ int64_t pack_upcat(std::vector<float>& out, const Folded& f) {
 }
 
 template <class C>
+Group make_thin(const char* name, int out_ch) {
+    Group g{};
+    g.name = name;
+    g.launch = &launch_thin<C>;
+    g.occupancy = &occ_thin<C>;
+    g.out_ch = out_ch;
+    return g;
+}
+
+template <class C>
 Group make_irbtc(const char* name, int out_ch) {
     Group g{};
     g.name = name;
@@ -620,7 +669,11 @@ static void build_plan(yf_ctx* ctx) {
         g.a.Hin = H; g.a.Win = W; g.a.Hout = H / 2; g.a.Wout = W / 2;
         g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
+#if YF_USE_THIN
+    chain(make_thin<CfgRes1Thin>("res1_1", 4), 2, 2);
+#else
     chain(make_irb<CfgRes1>("res1_1", 4), 2, 2);
+#endif
     { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense; g.occupancy = &occ_dense; g.out_ch = 8; chain(g, 2, 4); }
     chain(make_irb<CfgRes2>("res2_1", 8), 4, 4);
     chain(make_irb<CfgRes2>("res2_2", 8), 4, 4);
@@ -717,7 +770,11 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         cudaFuncSetAttribute(dense_kernel<CfgDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDense::SMEM_BYTES),
         cudaFuncSetAttribute(pw_kernel<CfgPw52>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPw52::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
-        init_irb<CfgRes1>(), init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
+        init_irb<CfgRes1>(),
+#if YF_USE_THIN
+        init_thin<CfgRes1Thin>(),
+#endif
+        init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
         init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
@@ -769,7 +826,11 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
         offs.push_back(pack_irb<C>(P, f, n + ".conv1", n + ".conv2", n + ".conv3", "", 0));
     };
     offs.push_back(pack_stem(P, f));
+#if YF_USE_THIN
+    offs.push_back(pack_thin<CfgRes1Thin>(P, f, "res1_1.conv1", "res1_1.conv2", "res1_1.conv3"));
+#else
     res(CfgRes1{}, "res1_1");
+#endif
     offs.push_back(pack_dense(P, f));
     res(CfgRes2{}, "res2_1"); res(CfgRes2{}, "res2_2");
     offs.push_back(pack_irb<CfgDown2>(P, f, "conv2_2", "conv2_3", "conv3_1", "", 0));
