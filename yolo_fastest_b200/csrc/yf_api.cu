@@ -280,7 +280,7 @@ using CfgUpCat = YF_CFGUPCAT;
 #endif
 using CfgNeckL1 = YF_CFGNECKL1;
 #ifndef YF_CFGNECKL2
-#define YF_CFGNECKL2 IrbCfg<96, 96, 96, 5, 1, 4, 40, 32, 4, 8, 4, 256, 2, false, false, false, false, 1>
+#define YF_CFGNECKL2 IrbCfg<96, 96, 96, 5, 1, 4, 40, 16, 4, 8, 4, 256, 2, false, false, false, false, 1>
 #endif
 using CfgNeckL2 = YF_CFGNECKL2;
 
@@ -379,7 +379,7 @@ int64_t pack_irb(std::vector<float>& out, const Folded& f, const std::string& n1
     pad4(out);
     const int64_t off = (int64_t)out.size();
     const int headp = rup(headn, 4);
-    out.resize(off + C::OFF_B2 + C::COUT + (C::HEADN > 0 ? C::COUT * headp + headp : 0), 0.f);
+    out.resize(off + (C::HEADC ? C::OFF_WH + C::CMIDP * headp + headp : C::OFF_B2 + C::COUT), 0.f);
     float* o = out.data() + off;
     for (int c = 0; c < C::NCHUNK; ++c) {
         float* cb = o + (int64_t)c * C::CB;
@@ -392,16 +392,27 @@ int64_t pack_irb(std::vector<float>& out, const Folded& f, const std::string& n1
             }
             for (int t = 0; t < C::KK; ++t) cb[C::OFF_WD + ml * C::KK + t] = f.w(nd)[m * C::KK + t];
             cb[C::OFF_BD + ml] = f.b(nd)[m];
-            for (int n = 0; n < C::COUT; ++n) cb[C::OFF_W2 + ml * C::COUT + n] = f.w(n2)[n * C::CMID + m];
+            if (!C::HEADC)
+                for (int n = 0; n < C::COUT; ++n) cb[C::OFF_W2 + ml * C::COUT + n] = f.w(n2)[n * C::CMID + m];
         }
     }
-    for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
-    if (C::HEADN > 0) {
-        float* wh = o + C::OFF_B2 + C::COUT;
-        float* bh = wh + C::COUT * headp;
-        for (int k = 0; k < C::COUT; ++k)
-            for (int n = 0; n < headn; ++n) wh[k * headp + n] = f.w(nh)[n * C::COUT + k];
-        for (int n = 0; n < headn; ++n) bh[n] = f.b(nh)[n];
+    if (!C::HEADC) {
+        for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
+    } else {
+        // n2 (conv5_6 / conv4_1_5: BN-folded 1x1, NO activation, yolo_fastest.py:136,146) followed by the biased head conv nh
+        // (:138,148) are two linear maps; compose them in double precision:  Wh' = Wh . W2,  bh' = Wh . b2 + bh
+        float* wh = o + C::OFF_WH;
+        float* bh = wh + C::CMIDP * headp;
+        for (int n = 0; n < headn; ++n) {
+            for (int m = 0; m < C::CMID; ++m) {
+                double a = 0.0;
+                for (int k = 0; k < C::COUT; ++k) a += (double)f.w(nh)[n * C::COUT + k] * (double)f.w(n2)[k * C::CMID + m];
+                wh[m * headp + n] = (float)a;
+            }
+            double b = (double)f.b(nh)[n];
+            for (int k = 0; k < C::COUT; ++k) b += (double)f.w(nh)[n * C::COUT + k] * (double)f.b(n2)[k];
+            bh[n] = (float)b;
+        }
     }
     return off;
 }

@@ -356,8 +356,8 @@ __device__ __forceinline__ TileId tile_id(int tiles_x, int tiles_y) {
 // conv4_2/conv4_3/conv5_1 with the conv4_2 skip output (:121-124,190), and with EXPAND=false the
 // neck pairs dw5x5 -> 1x1 (:133-136,143-146) including the biased head convs (:138,148).
 // Packed weights (floats): NCHUNK x { [W1: CIN*MC][b1: MC] (EXPAND only) [Wd: MC*KS*KS][bd: MC][W2: MC*COUT] },
-// then [b2: COUT], then (HEADN > 0: group ends in a head conv) [Wh: COUT*headp][bh: headp] with headp = rup(headn, 4),
-// headn = num_anchors * (5 + num_cls) given at run time.
+// then [b2: COUT]. Head groups (HEADN > 0) carry no W2/b2: after the chunk blocks come the composed head weights
+// [Wh': CMIDP*headp][bh': headp], headp = rup(headn, 4), headn = num_anchors * (5 + num_cls) given at run time.
 // ---------------------------------------------------------------------------------------------
 template <int CIN_, int CMID_, int COUT_, int KS_, int S_, int TH_, int TW_, int MC_, int PN1_, int PN3_, int RH_,
           int NT_, int MINB_, bool EXPAND_, bool RES_, bool RELU_OUT_, bool DUAL_, int HEADN_ = 0, int XBUF_ = 1>
@@ -370,20 +370,25 @@ struct IrbCfg {
     static constexpr int KK = KS_ * KS_;
     static constexpr int CMIDP = rup(CMID, MC);
     static constexpr int NCHUNK = CMIDP / MC;
+    // HEADN > 0: the group ends in a biased 1x1 head conv (yolo_fastest.py:138,148). The 1x1 before it (conv5_6 / conv4_1_5) has no
+    // activation, so the two linear maps are composed on the host into ONE [CMID][headp] matrix (yf_api.cu: pack_irb) and the
+    // engine runs depthwise -> composed head: the depthwise output of ALL mid channels stays in smem (Os) and is contracted once.
+    static constexpr bool HEADC = HEADN > 0;
     static constexpr int OFF_W1 = 0;
     static constexpr int OFF_B1 = OFF_W1 + (EXPAND ? CIN * MC : 0);
     static constexpr int OFF_WD = OFF_B1 + (EXPAND ? MC : 0);
     static constexpr int OFF_BD = OFF_WD + MC * KK;
     static constexpr int OFF_W2 = OFF_BD + MC;
-    static constexpr int CB = OFF_W2 + MC * COUT;              // floats per chunk block
+    static constexpr int CB = OFF_W2 + (HEADC ? 0 : MC * COUT);              // floats per chunk block
     static constexpr int OFF_B2 = NCHUNK * CB;
-    static constexpr int OFF_WH = OFF_B2 + COUT;             // head weights [COUT][headp], then bias [headp] (runtime headn)
+    static constexpr int OFF_WH = HEADC ? OFF_B2 : OFF_B2 + COUT;             // composed head weights [CMIDP][headp], then bias [headp] (runtime headn)
     // shared memory (floats); every region starts 128B aligned
     static constexpr int XS1 = EXPAND ? rup(CIN * G::IPIX, 32) : 0;   // one input halo tile [CIN][IH][IWS]
     static constexpr int XS = XBUF * XS1;
     static constexpr int ES = rup(MC * G::IPIX, 32);
-    static constexpr int DS = rup(MC * G::OPIX, 32);
-    static constexpr int ACT = cmax(XS + ES + DS, HEADN > 0 ? rup(COUT * G::OPIX, 32) : 0);
+    static constexpr int EBUF = HEADC ? 2 : 1;                         // staged-chunk buffers (HEADC has no 1x1 phase to hide the next chunk's copy behind)
+    static constexpr int DS = HEADC ? rup(CMIDP * G::OPIX, 32) : rup(MC * G::OPIX, 32);
+    static constexpr int ACT = XS + EBUF * ES + DS;
     static constexpr int WS1 = rup(CB, 32);
     static constexpr int SMEM_FLOATS = ACT + 2 * WS1;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
@@ -393,6 +398,7 @@ struct IrbCfg {
     static_assert(MC % 4 == 0 && COUT % 4 == 0 && CB % 4 == 0, "alignment");
     static_assert(!RES || (CIN == COUT && S_ == 1 && EXPAND), "residual needs same shape");
     static_assert(EXPAND || (CMID == CIN && CIN % MC == 0), "dw-first groups have CMID == CIN, a multiple of MC");
+    static_assert(!HEADC || !EXPAND, "head groups are depthwise-first");
     static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
     static_assert(XBUF == 1 || XBUF == 2, "one or two input-tile buffers");
 };
@@ -409,8 +415,8 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bars[2];     // weight buffers
     float* Xs0 = smem;
-    float* Es = smem + C::XS;
-    float* Ds = Es + C::ES;
+    float* Es0 = smem + C::XS;
+    float* Ds = Es0 + C::EBUF * C::ES;             // HEADC: depthwise output of all mid channels [CMIDP][OPIX]
     float* Ws = smem + C::ACT;
     const int tid = threadIdx.x;
 
@@ -443,10 +449,11 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
     __syncthreads();
     if (tile < total_tiles) {
         if (tid == 0) issue_w(0, 0);
-        stage_tile(tile, 0, C::EXPAND ? Xs0 : Es);
+        stage_tile(tile, 0, C::EXPAND ? Xs0 : Es0);
     }
 
     uint32_t q = 0;      // running chunk sequence number of this CTA (weight buffer q & 1, parity (q >> 1) & 1)
+    uint32_t eq = 0;     // running staged-chunk number (HEADC: staging buffer eq & 1)
     for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
         int tb, oy0, ox0;
         tile_origin(tile, tb, oy0, ox0);
@@ -490,6 +497,16 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
             }
             if (C::NCHUNK > 1) mbar_wait(&bars[wbuf], (q >> 1) & 1);
             else if (it == 0) mbar_wait(&bars[0], 0);
+            float* Es = Es0 + (C::HEADC ? (eq & 1) * C::ES : 0);
+            if (C::HEADC) {
+                // the next channel chunk (or chunk 0 of the next tile) flies into the other staging buffer during this chunk's depthwise
+                float* En = Es0 + ((eq + 1) & 1) * C::ES;
+                if (c + 1 < C::NCHUNK) stage_tile(tile, (c + 1) * C::MC, En);
+                else if (have_next) stage_tile(tile + gridDim.x, 0, En);
+                ++eq;
+                dw_stage<G, C::MC, C::RH, NT>(Es, Wc + C::OFF_WD, Wc + C::OFF_BD, Ds + c * C::MC * G::OPIX);
+                continue;
+            }
             if (C::EXPAND) {
                 float* sk = C::DUAL ? skip + ((size_t)tb * C::CMID + c * C::MC) * Hin * Win : nullptr;
                 pw_halo<G, C::CIN, C::MC, C::PN1, NT, C::DUAL>(Xs, Wc + C::OFF_W1, Wc + C::OFF_B1, Es, iy0, ix0, Hin, Win,
@@ -500,17 +517,52 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
             dw_stage<G, C::MC, C::RH, NT>(Es, Wc + C::OFF_WD, Wc + C::OFF_BD, Ds);
             __syncthreads();   // (C) D complete, E free
             if (!C::EXPAND) {
-                // the next E chunk (next channel chunk of this tile, or chunk 0 of the next tile) flies during the 1x1 below;
-                // a head epilogue reuses the E region, so there chunk 0 of the next tile is staged after it
+                // the next E chunk (next channel chunk of this tile, or chunk 0 of the next tile) flies during the 1x1 below
                 if (c + 1 < C::NCHUNK) stage_tile(tile, (c + 1) * C::MC, Es);
-                else if (have_next && C::HEADN == 0) stage_tile(tile + gridDim.x, 0, Es);
+                else if (have_next) stage_tile(tile + gridDim.x, 0, Es);
             }
             pw_accum<G::OPIX, C::MC, C::COUT, C::PN3, C::IPT, NT>(Ds, Wc + C::OFF_W2, acc);
         }
 
+        if (C::HEADC) {
+            // composed head: out[n] = sum_m Wh'[m][n] * D[m] + bh'[n] over ALL mid channels (the 1x1 before the head and the head
+            // itself, yolo_fastest.py:136-138 / 146-148, folded into one matrix on the host); weights are read through L1.
+            __syncthreads();               // D of every chunk is complete
+            const int headp = (headn + 3) & ~3;
+            const float* Wh = wts + C::OFF_WH;
+            const float* bh = Wh + C::CMIDP * headp;
+            constexpr int NPG = G::OPIX / 4;
+            const int NCGH = headp / 4;
+            for (int item = tid; item < NPG * NCGH; item += NT) {
+                const int cg = item / NPG;
+                const int pg = item - cg * NPG;
+                const int p0 = pg * 4;
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bh + cg * 4));
+                float a[4][4] = {{bb.x, bb.x, bb.x, bb.x}, {bb.y, bb.y, bb.y, bb.y}, {bb.z, bb.z, bb.z, bb.z}, {bb.w, bb.w, bb.w, bb.w}};
+#pragma unroll 8
+                for (int k = 0; k < C::CMIDP; ++k) {
+                    const float4 ov = ld4(Ds + k * G::OPIX + p0);
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(Wh + k * headp + cg * 4));
+                    const float o4[4] = {ov.x, ov.y, ov.z, ov.w};
+                    const float w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) a[qq][j] = fmaf(w4[qq], o4[j], a[qq][j]);
+                }
+                const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
+                const int gy = oy0 + oy, gx0 = ox0 + ox;
+                if (gy < Hout) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int ch = cg * 4 + qq;
+                        if (ch < headn) store_px4(y + (((size_t)tb * headn + ch) * Hout + gy) * Wout, gx0, Wout, a[qq]);
+                    }
+                }
+            }
+            continue;                      // the next tile's first sync (A) orders these reads before its depthwise writes D again
+        }
         const float* b2 = wts + C::OFF_B2;
-        if (C::HEADN > 0) __syncthreads();   // Ds/Es are about to be reused as the projected tile
-        float* Os = smem;                    // [COUT][OPIX] (HEADN > 0 only)
 #pragma unroll
         for (int i = 0; i < C::IPT; ++i) {
             const int item = tid + i * NT;
@@ -531,53 +583,8 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
 #pragma unroll
                         for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-                    if (C::HEADN > 0) {
-                        st4(Os + ch * G::OPIX + p0, make_float4(v[0], v[1], v[2], v[3]));
-                    } else if (gy < Hout) {
-                        store_px4(y + (((size_t)tb * C::COUT + ch) * Hout + gy) * Wout, gx0, Wout, v);
-                    }
+                    if (gy < Hout) store_px4(y + (((size_t)tb * C::COUT + ch) * Hout + gy) * Wout, gx0, Wout, v);
                 }
-            }
-        }
-        if (C::HEADN > 0) {
-            // biased 1x1 head conv (yolo_fastest.py:138,148) straight from the projected tile in smem;
-            // head weights [COUT][headp] are read through L1 (warp-broadcast).
-            __syncthreads();
-            const int headp = (headn + 3) & ~3;
-            const float* Wh = wts + C::OFF_WH;
-            const float* bh = Wh + C::COUT * headp;
-            constexpr int NPG = G::OPIX / 4;
-            const int NCGH = headp / 4;
-            for (int item = tid; item < NPG * NCGH; item += NT) {
-                const int cg = item / NPG;
-                const int pg = item - cg * NPG;
-                const int p0 = pg * 4;
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bh + cg * 4));
-                float a[4][4] = {{bb.x, bb.x, bb.x, bb.x}, {bb.y, bb.y, bb.y, bb.y}, {bb.z, bb.z, bb.z, bb.z}, {bb.w, bb.w, bb.w, bb.w}};
-#pragma unroll 8
-                for (int k = 0; k < C::COUT; ++k) {
-                    const float4 ov = ld4(Os + k * G::OPIX + p0);
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(Wh + k * headp + cg * 4));
-                    const float o4[4] = {ov.x, ov.y, ov.z, ov.w};
-                    const float w4[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) a[qq][j] = fmaf(w4[qq], o4[j], a[qq][j]);
-                }
-                const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
-                const int gy = oy0 + oy, gx0 = ox0 + ox;
-                if (gy < Hout) {
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const int ch = cg * 4 + qq;
-                        if (ch < headn) store_px4(y + (((size_t)tb * headn + ch) * Hout + gy) * Wout, gx0, Wout, a[qq]);
-                    }
-                }
-            }
-            if (have_next) {
-                __syncthreads();           // the projected tile (aliasing E) has been consumed
-                stage_tile(tile + gridDim.x, 0, Es);
             }
         }
     }
