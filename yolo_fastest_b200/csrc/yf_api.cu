@@ -16,6 +16,7 @@
 #include "yf_post.cuh"
 #include "yf_tc.cuh"
 #include "yf_thin.cuh"
+#include "yf_tcpw.cuh"
 
 using namespace yf;
 
@@ -283,6 +284,15 @@ using CfgNeckL1 = YF_CFGNECKL1;
 #define YF_CFGNECKL2 IrbCfg<96, 96, 96, 5, 1, 4, 40, 16, 4, 8, 4, 256, 2, false, false, false, false, 1>
 #endif
 using CfgNeckL2 = YF_CFGNECKL2;
+// tensor-core depthwise -> wide 1x1 pairs of the neck: DwPwTcCfg<C, N, KS, TH, TW, MC, RH, worker warps, RELU>
+#ifndef YF_CFGNECKS1_TC
+#define YF_CFGNECKS1_TC DwPwTcCfg<96, 128, 5, 16, 20, 16, 4, 10, false>
+#endif
+using CfgNeckS1Tc = YF_CFGNECKS1_TC;
+#ifndef YF_CFGNECKL1_TC
+#define YF_CFGNECKL1_TC DwPwTcCfg<96, 96, 5, 8, 40, 16, 4, 10, false>
+#endif
+using CfgNeckL1Tc = YF_CFGNECKL1_TC;
 
 namespace {
 
@@ -315,6 +325,18 @@ void launch_thin(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) 
 template <class C> int occ_thin() { return occ_of(thin_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
 cudaError_t init_thin() { return cudaFuncSetAttribute(thin_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
+
+template <class C>
+void launch_dwpwtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using G = typename C::G;
+    const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    dwpw_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+}
+template <class C> int occ_dwpwtc() { return occ_of(dwpw_tc_kernel<C>, C::NT, C::SMEM_BYTES); }
+template <class C>
+cudaError_t init_dwpwtc() { return cudaFuncSetAttribute(dwpw_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
 
 template <class C>
 void launch_irbtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
@@ -451,6 +473,26 @@ int64_t pack_thin(std::vector<float>& out, const Folded& f, const std::string& n
 }
 
 template <class C>
+int64_t pack_dwpwtc(std::vector<float>& out, const Folded& f, const std::string& nd, const std::string& n2) {
+    pad4(out);
+    while (out.size() % 32) out.push_back(0.f);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int c = 0; c < C::NCHUNK; ++c) {
+        float* cb = o + (int64_t)c * C::CB;
+        for (int ml = 0; ml < C::MC; ++ml) {
+            const int m = c * C::MC + ml;
+            for (int t = 0; t < C::KK; ++t) cb[C::OFF_WD + ml * C::KK + t] = f.w(nd)[m * C::KK + t];
+            cb[C::OFF_BD + ml] = f.b(nd)[m];
+            for (int n = 0; n < C::N; ++n) put_kmajor_split(cb + C::OFF_WH, cb + C::OFF_WL, n, ml, C::MC, f.w(n2)[n * C::C + m]);
+        }
+    }
+    for (int n = 0; n < C::N; ++n) o[C::OFF_B + n] = f.b(n2)[n];
+    return off;
+}
+
+template <class C>
 int64_t pack_irbtc(std::vector<float>& out, const Folded& f, const std::string& n1, const std::string& nd, const std::string& n2) {
     pad4(out);
     while (out.size() % 32) out.push_back(0.f);          // bulk copies and UMMA descriptors want 128-byte aligned blocks
@@ -567,6 +609,16 @@ Group make_thin(const char* name, int out_ch) {
     g.name = name;
     g.launch = &launch_thin<C>;
     g.occupancy = &occ_thin<C>;
+    g.out_ch = out_ch;
+    return g;
+}
+
+template <class C>
+Group make_dwpwtc(const char* name, int out_ch) {
+    Group g{};
+    g.name = name;
+    g.launch = &launch_dwpwtc<C>;
+    g.occupancy = &occ_dwpwtc<C>;
     g.out_ch = out_ch;
     return g;
 }
@@ -727,7 +779,11 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes5>("res5_5", 48), 32, 32);
     { Group g{}; g.name = "conv5_2"; g.launch = &launch_pw52; g.out_ch = 96; chain(g, 32, 32); }
     const float* conv5_2 = prev;
+#if YF_USE_TC
+    chain(make_dwpwtc<CfgNeckS1Tc>("conv5_4", 128), 32, 32);
+#else
     chain(make_irb<CfgNeckS1>("conv5_4", 128), 32, 32);
+#endif
     {
         Group g = make_irb<CfgNeckS2>("head_5", 0);   // y = caller's head_small, set per call
         hw(g, 32, 32); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
@@ -736,7 +792,11 @@ static void build_plan(yf_ctx* ctx) {
         Group g{}; g.name = "conv4_1_1"; g.launch = &launch_upcat; g.occupancy = &occ_upcat; g.out_ch = 96;
         hw(g, 16, 16); g.a.x = ctx->d_skip; g.a.x2 = conv5_2; g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
+#if YF_USE_TC
+    chain(make_dwpwtc<CfgNeckL1Tc>("conv4_1_3", 96), 16, 16);
+#else
     chain(make_irb<CfgNeckL1>("conv4_1_3", 96), 16, 16);
+#endif
     {
         Group g = make_irb<CfgNeckL2>("head_4", 0);   // y = caller's head_large
         hw(g, 16, 16); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
@@ -786,7 +846,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         init_thin<CfgRes1Thin>(),
 #endif
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -863,10 +923,18 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     offs.push_back(pack_irb<CfgDown4>(P, f, "conv4_2", "conv4_3", "conv5_1", "", 0));
     res(CfgRes5{}, "res5_1"); res(CfgRes5{}, "res5_2"); res(CfgRes5{}, "res5_3"); res(CfgRes5{}, "res5_4"); res(CfgRes5{}, "res5_5");
     offs.push_back(pack_pw52(P, f));
+#if YF_USE_TC
+    offs.push_back(pack_dwpwtc<CfgNeckS1Tc>(P, f, "conv5_3", "conv5_4"));
+#else
     offs.push_back(pack_irb<CfgNeckS1>(P, f, "", "conv5_3", "conv5_4", "", 0));
+#endif
     offs.push_back(pack_irb<CfgNeckS2>(P, f, "", "conv5_5", "conv5_6", "head_5", ctx->nout));
     offs.push_back(pack_upcat(P, f));
+#if YF_USE_TC
+    offs.push_back(pack_dwpwtc<CfgNeckL1Tc>(P, f, "conv4_1_2", "conv4_1_3"));
+#else
     offs.push_back(pack_irb<CfgNeckL1>(P, f, "", "conv4_1_2", "conv4_1_3", "", 0));
+#endif
     offs.push_back(pack_irb<CfgNeckL2>(P, f, "", "conv4_1_4", "conv4_1_5", "head_4", ctx->nout));
     pad4(P);
     if (offs.size() != ctx->groups.size()) { set_err(&ctx->err, "internal: %zu packs vs %zu groups", offs.size(), ctx->groups.size()); return YF_ERR_STATE; }
