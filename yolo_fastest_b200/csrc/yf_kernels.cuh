@@ -16,6 +16,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifndef YF_FFMA2
+#define YF_FFMA2 1
+#endif
 
 namespace yf {
 
@@ -43,6 +46,17 @@ struct Geo {
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// Two FMAs in one issue slot (fma.rn.f32x2 -> FFMA2, sm_100+): (a0, a1) += (w0, w1) * x. Per-lane rounding is the scalar fmaf's, so
+// results are bit-identical; the register-tiled 1x1 loops below are issue-bound, and pairing the accumulators over adjacent output
+// channels (weights arrive as natural pairs from 128-bit loads) raises their FMA rate by ~15% (tools/selftest/ffma2_bench.cu).
+__device__ __forceinline__ void ffma2(float w0, float w1, float x, float& a0, float& a1) {
+#if YF_FFMA2
+    const float2 r = __ffma2_rn(make_float2(w0, w1), make_float2(x, x), make_float2(a0, a1));
+    a0 = r.x; a1 = r.y;
+#else
+    a0 = fmaf(w0, x, a0); a1 = fmaf(w1, x, a1);
+#endif
+}
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // Cooperative copy of n floats (n % 4 == 0, both 16B aligned) global -> shared.
@@ -182,9 +196,9 @@ __device__ __forceinline__ void pw_halo(const float* __restrict__ Xs, const floa
                     const float4 w = ld4(wp + k * MC + n4 * 4);
                     const float w4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < 4; q += 2)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[n4 * 4 + q][i] = fmaf(w4[q], x4[i], acc[n4 * 4 + q][i]);
+                        for (int i = 0; i < 4; ++i) ffma2(w4[q], w4[q + 1], x4[i], acc[n4 * 4 + q][i], acc[n4 * 4 + q + 1][i]);
                 }
             }
         }
@@ -319,9 +333,9 @@ __device__ __forceinline__ void pw_accum(const float* __restrict__ Ds, const flo
                     const float4 w = ld4(wp + m * N + n4 * 4);
                     const float w4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < 4; q += 2)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[it][n4 * 4 + q][i] = fmaf(w4[q], d4[i], acc[it][n4 * 4 + q][i]);
+                        for (int i = 0; i < 4; ++i) ffma2(w4[q], w4[q + 1], d4[i], acc[it][n4 * 4 + q][i], acc[it][n4 * 4 + q + 1][i]);
                 }
             }
         }
@@ -546,9 +560,9 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
                     const float o4[4] = {ov.x, ov.y, ov.z, ov.w};
                     const float w4[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq)
+                    for (int qq = 0; qq < 4; qq += 2)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) a[qq][j] = fmaf(w4[qq], o4[j], a[qq][j]);
+                        for (int j = 0; j < 4; ++j) ffma2(w4[qq], w4[qq + 1], o4[j], a[qq][j], a[qq + 1][j]);
                 }
                 const int oy = p0 / G::TW, ox = p0 - oy * G::TW;
                 const int gy = oy0 + oy, gx0 = ox0 + ox;
@@ -852,9 +866,9 @@ dense_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                                for (int n = 0; n < 8; ++n)
+                                for (int n = 0; n < 8; n += 2)
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) acc[i][n][j] = fmaf(w8[dx][n], v[2 * j + dx], acc[i][n][j]);
+                                    for (int j = 0; j < 4; ++j) ffma2(w8[dx][n], w8[dx][n + 1], v[2 * j + dx], acc[i][n][j], acc[i][n + 1][j]);
                         }
                     }
                 }
