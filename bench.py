@@ -70,10 +70,12 @@ def group_work(H, W, nout):
         add(n, irb(48, 224, 32), [(48, 32)], [(48, 32)])
     add("conv5_2", [pw(48, 96, 32)], [(48, 32)], [(96, 32)])
     add("conv5_4", [dw(96, 5, 32), pw(96, 128, 32)], [(96, 32)], [(128, 32)])
-    add("head_5", [dw(128, 5, 32), pw(128, 128, 32), pw(128, nout, 32)], [(128, 32)], [(nout, 32)])
+    # the 1x1 before each head has no activation: it is composed with the head conv on the host (yf_api.cu: pack_irb), so the
+    # executed work is depthwise + ONE 1x1; counting the reference's two 1x1s would overstate the achieved FLOP rate
+    add("head_5", [dw(128, 5, 32), pw(128, nout, 32)], [(128, 32)], [(nout, 32)])
     add("conv4_1_1", [(px(16) * 96 * 96, 96 * 96 * 4 + 96), pw(232, 96, 16)], [(136, 16), (96, 32)], [(96, 16)])
     add("conv4_1_3", [dw(96, 5, 16), pw(96, 96, 16)], [(96, 16)], [(96, 16)])
-    add("head_4", [dw(96, 5, 16), pw(96, 96, 16), pw(96, nout, 16)], [(96, 16)], [(nout, 16)])
+    add("head_4", [dw(96, 5, 16), pw(96, nout, 16)], [(96, 16)], [(nout, 16)])
     return G
 
 
@@ -328,7 +330,16 @@ def main():
         kernels.append({"name": name, "ms": round(m, 4), "share": round(m / total_ms, 4), "GB/s": round(gbs, 1), "hbm_frac": round(gbs / hbm_peak, 4),
                         "TFLOP/s": round(tfl, 2), "fp32_frac": round(tfl / FP32_PEAK_TFLOPS, 4)})
     top = max(kernels, key=lambda k: k["ms"])
-    roofline = {"bound": "hbm", "achieved": top["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": None,
+    # DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu pass
+    # of this same workload (tools/launch_report.py -> profiles/r01_traffic.json); null when no capture matches the workload
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr.get("workload") == "%dx%d b%d" % (W, H, B):
+            traffic = tr["bytes_per_launch"].get(top["name"])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": top["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": traffic,
                 "kernel": top["name"], "share_of_forward": top["share"], "peak_source": peak_src,
                 "note": "fused groups are FP32 CUDA-core bound (48 FLOP/B overall); see fp32"}
     fp32 = {"kernel": top["name"], "achieved": top["TFLOP/s"], "peak": round(FP32_PEAK_TFLOPS, 1), "unit": "TFLOP/s", "frac": top["fp32_frac"],

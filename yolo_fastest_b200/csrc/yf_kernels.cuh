@@ -623,7 +623,8 @@ struct StemCfg {
     static constexpr int RS = RH * RWS;
     static constexpr int NPRE = cdiv(RS, NT_);
     static constexpr int XS = 8 * G::IPIX, ES = 8 * G::IPIX, DS = 8 * G::OPIX;
-    static constexpr int SMEM_FLOATS = RS + XS + ES + DS + WFLOATS;
+    static constexpr int WPAD = rup(WFLOATS, 4);
+    static constexpr int SMEM_FLOATS = RS + XS + ES + DS + WPAD + 256;   // + the uint8 -> (x - 128) / 255 table
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
     static constexpr int IPT = cdiv(G::OPIX / 4, NT);
     static_assert(SMEM_BYTES <= 227 * 1024, "stem tile too large");
@@ -642,7 +643,12 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
     float* Es = Xs + C::XS;
     float* Ds = Es + C::ES;
     float* Ws = Ds + C::DS;
-    // fetch this thread's share of a tile's raw rectangle into registers (normalising uint8 on the fly)
+    float* Lut = Ws + C::WPAD;       // U8IN: (u - 128) / 255 for u = 0..255, the reference's fp32 division done once (detect.py:124)
+    if (U8IN) {
+        for (int i = threadIdx.x; i < 256; i += NT) Lut[i] = ((float)i - 128.0f) / 255.0f;
+        __syncthreads();
+    }
+    // fetch this thread's share of a tile's raw rectangle into registers (normalising uint8 through the table)
     auto fetch_raw = [&](int tile, float (&pre)[NPRE]) {
         const int tx = tile % tiles_x;
         const int r0 = tile / tiles_x;
@@ -656,7 +662,7 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
             float v = 0.f;
             if (idx < C::RS && j < C::RW && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win) {
                 const size_t off = ((size_t)b * Hin + gy) * Win + gx;
-                if (U8IN) v = ((float)__ldg(reinterpret_cast<const unsigned char*>(xin) + off) - 128.0f) / 255.0f;
+                if (U8IN) v = Lut[__ldg(reinterpret_cast<const unsigned char*>(xin) + off)];
                 else v = __ldg(reinterpret_cast<const float*>(xin) + off);
             }
             pre[k] = v;
