@@ -90,7 +90,10 @@ constexpr int pow2_ge(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 // step for the first 64 steps; read back through yf_debug_trace (tools/tc_trace.py). Compiled out otherwise.
 #ifdef YF_TC_TRACE
 __device__ long long g_tc_trace[16 * 64];
-#define TC_TRACE(step, ev) do { if (blockIdx.x == 0 && (step) < 64) g_tc_trace[(step) * 16 + (ev)] = clock64(); } while (0)
+#ifndef YF_TC_TRACE_CMID
+#define YF_TC_TRACE_CMID 96          // which instantiation records (mid channels): 96 = res3_3..6, 136 = res4_1..4
+#endif
+#define TC_TRACE(step, ev) do { if (C::CMID == YF_TC_TRACE_CMID && blockIdx.x == 0 && (step) < 64) g_tc_trace[(step) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define TC_TRACE(step, ev) do { } while (0)
 #endif
