@@ -17,6 +17,7 @@
 #include "yf_tc.cuh"
 #include "yf_thin.cuh"
 #include "yf_tcpw.cuh"
+#include "yf_tcup.cuh"
 
 using namespace yf;
 
@@ -293,6 +294,10 @@ using CfgNeckS1Tc = YF_CFGNECKS1_TC;
 #define YF_CFGNECKL1_TC DwPwTcCfg<96, 96, 5, 8, 40, 16, 4, 10, false>
 #endif
 using CfgNeckL1Tc = YF_CFGNECKL1_TC;
+using CfgUpCatTc = UpCatTcCfg<10>;
+// the tensor-core upsample+concat kernel moves the skip tensor with 128-bit loads: it needs the 1/16-resolution map to be a
+// multiple of 4 wide and even in height (true for the shipped 512x640 / 256x320 models; 416x416 falls back to upcat_kernel)
+static bool upcat_on_tc(int H, int W) { return YF_USE_TC && ((W / 16) % 4 == 0) && ((H / 16) % 2 == 0); }
 
 namespace {
 
@@ -314,6 +319,14 @@ template <class C> int occ_irb() { return occ_of(irb_kernel<C>, C::NT, C::SMEM_B
 int occ_stem() { return occ_of(stem_kernel<CfgStem, false>, CfgStem::NT, CfgStem::SMEM_BYTES); }
 int occ_dense() { return occ_of(dense_kernel<CfgDense>, CfgDense::NT, CfgDense::SMEM_BYTES); }
 int occ_upcat() { return occ_of(upcat_kernel<CfgUpCat>, CfgUpCat::NT, CfgUpCat::SMEM_BYTES); }
+int occ_upcat_tc() { return occ_of(upcat_tc_kernel<CfgUpCatTc>, CfgUpCatTc::NT, CfgUpCatTc::SMEM_BYTES); }
+void launch_upcat_tc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using C = CfgUpCatTc;
+    const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    upcat_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.x2, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+}
 
 template <class C>
 void launch_thin(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
@@ -469,6 +482,44 @@ int64_t pack_thin(std::vector<float>& out, const Folded& f, const std::string& n
         for (int n = 0; n < C::COUT; ++n) wm[C::OFF_W2 + n] = f.w(n2)[n * C::CMID + m];
     }
     for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
+    return off;
+}
+
+// weight slots of upcat_tc_kernel in its step order: A(half 0) x 6 | 9 skip chunks | 3 up chunks | A(half 1) x 6 | 3 up chunks
+int64_t pack_upcat_tc(std::vector<float>& out, const Folded& f) {
+    using C = CfgUpCatTc;
+    pad4(out);
+    while (out.size() % 32) out.push_back(0.f);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    const float* w = f.w("conv4_1_1");    // [96][232]
+    const float* wt = f.w("deconv5_1");   // [cin 96][cout 96][2][2]
+    int slot = 0;
+    auto a_steps = [&](int h) {
+        for (int kc = 0; kc < C::NKA; ++kc, ++slot) {
+            float* sb = o + (int64_t)slot * C::SLOT;
+            for (int par = 0; par < 4; ++par)
+                for (int ml = 0; ml < 48; ++ml)
+                    for (int kl = 0; kl < C::MC; ++kl) {
+                        const int c = kc * C::MC + kl, m = 48 * h + ml;
+                        put_kmajor_split(sb, sb + C::NHALF * C::MC, par * 48 + ml, kl, C::MC, wt[((c * 96 + m) * 2 + (par >> 1)) * 2 + (par & 1)]);
+                    }
+        }
+    };
+    auto b_step = [&](int k0, int kvalid) {      // concat rows [k0, k0 + 16), the first kvalid of them real
+        float* sb = o + (int64_t)slot * C::SLOT;
+        for (int n = 0; n < C::N; ++n)
+            for (int kl = 0; kl < kvalid; ++kl) put_kmajor_split(sb, sb + C::N * C::MC, n, kl, C::MC, w[n * 232 + k0 + kl]);
+        ++slot;
+    };
+    a_steps(0);
+    for (int c = 0; c < C::NSKIP; ++c) b_step(c * C::MC, std::min(C::MC, C::CS - c * C::MC));
+    for (int j = 0; j < C::NUPH; ++j) b_step(C::CS + j * C::MC, C::MC);
+    a_steps(1);
+    for (int j = 0; j < C::NUPH; ++j) b_step(C::CS + 48 + j * C::MC, C::MC);
+    for (int m = 0; m < 96; ++m) o[C::OFF_BT + m] = f.b("deconv5_1")[m];
+    for (int n = 0; n < 96; ++n) o[C::OFF_B + n] = f.b("conv4_1_1")[n];
     return off;
 }
 
@@ -789,7 +840,9 @@ static void build_plan(yf_ctx* ctx) {
         hw(g, 32, 32); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
     {
-        Group g{}; g.name = "conv4_1_1"; g.launch = &launch_upcat; g.occupancy = &occ_upcat; g.out_ch = 96;
+        Group g{}; g.name = "conv4_1_1"; g.out_ch = 96;
+        if (upcat_on_tc(ctx->H, ctx->W)) { g.launch = &launch_upcat_tc; g.occupancy = &occ_upcat_tc; }
+        else { g.launch = &launch_upcat; g.occupancy = &occ_upcat; }
         hw(g, 16, 16); g.a.x = ctx->d_skip; g.a.x2 = conv5_2; g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
 #if YF_USE_TC
@@ -841,6 +894,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         cudaFuncSetAttribute(dense_kernel<CfgDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDense::SMEM_BYTES),
         cudaFuncSetAttribute(pw_kernel<CfgPw52>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPw52::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
+        cudaFuncSetAttribute(upcat_tc_kernel<CfgUpCatTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCatTc::SMEM_BYTES),
         init_irb<CfgRes1>(),
 #if YF_USE_THIN
         init_thin<CfgRes1Thin>(),
@@ -929,7 +983,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     offs.push_back(pack_irb<CfgNeckS1>(P, f, "", "conv5_3", "conv5_4", "", 0));
 #endif
     offs.push_back(pack_irb<CfgNeckS2>(P, f, "", "conv5_5", "conv5_6", "head_5", ctx->nout));
-    offs.push_back(pack_upcat(P, f));
+    offs.push_back(upcat_on_tc(ctx->H, ctx->W) ? pack_upcat_tc(P, f) : pack_upcat(P, f));
 #if YF_USE_TC
     offs.push_back(pack_dwpwtc<CfgNeckL1Tc>(P, f, "conv4_1_2", "conv4_1_3"));
 #else
