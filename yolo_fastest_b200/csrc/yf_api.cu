@@ -18,6 +18,7 @@
 #include "yf_thin.cuh"
 #include "yf_tcpw.cuh"
 #include "yf_tcup.cuh"
+#include "yf_tcirb2.cuh"
 
 using namespace yf;
 
@@ -295,6 +296,11 @@ using CfgNeckS1Tc = YF_CFGNECKS1_TC;
 #endif
 using CfgNeckL1Tc = YF_CFGNECKL1_TC;
 using CfgUpCatTc = UpCatTcCfg<10>;
+// widest residual blocks on the chunked tensor-core engine: IrbTc2Cfg<CIN, CMID, COUT, TH, TW, N halves, RH, worker warps, RES>
+#ifndef YF_CFGRES5_TC
+#define YF_CFGRES5_TC IrbTc2Cfg<48, 224, 48, 8, 20, 2, 2, 10, true>
+#endif
+using CfgRes5Tc = YF_CFGRES5_TC;
 // the tensor-core upsample+concat kernel moves the skip tensor with 128-bit loads: it needs the 1/16-resolution map to be a
 // multiple of 4 wide and even in height (true for the shipped 512x640 / 256x320 models; 416x416 falls back to upcat_kernel)
 static bool upcat_on_tc(int H, int W) { return YF_USE_TC && ((W / 16) % 4 == 0) && ((H / 16) % 2 == 0); }
@@ -350,6 +356,18 @@ void launch_dwpwtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st
 template <class C> int occ_dwpwtc() { return occ_of(dwpw_tc_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
 cudaError_t init_dwpwtc() { return cudaFuncSetAttribute(dwpw_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
+
+template <class C>
+void launch_irbtc2(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using G = typename C::G;
+    const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    irbtc2_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+}
+template <class C> int occ_irbtc2() { return occ_of(irbtc2_kernel<C>, C::NT, C::SMEM_BYTES); }
+template <class C>
+cudaError_t init_irbtc2() { return cudaFuncSetAttribute(irbtc2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
 
 template <class C>
 void launch_irbtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
@@ -523,6 +541,40 @@ int64_t pack_upcat_tc(std::vector<float>& out, const Folded& f) {
     return off;
 }
 
+// weight slots of irbtc2_kernel in its step order: per half { CIN/16 expand K chunks | CMID/NH/16 mid chunks }
+template <class C>
+int64_t pack_irbtc2(std::vector<float>& out, const Folded& f, const std::string& n1, const std::string& nd, const std::string& n2) {
+    pad4(out);
+    while (out.size() % 32) out.push_back(0.f);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    int slot = 0;
+    for (int h = 0; h < C::NH; ++h) {
+        for (int kc = 0; kc < C::NKA; ++kc, ++slot) {
+            float* sb = o + (int64_t)slot * C::SLOT;
+            for (int ml = 0; ml < C::NA; ++ml) {
+                const int m = h * C::NA + ml;
+                if (m >= C::CMID) continue;
+                for (int kl = 0; kl < C::MC; ++kl) put_kmajor_split(sb, sb + C::NA * C::MC, ml, kl, C::MC, f.w(n1)[m * C::CIN + kc * C::MC + kl]);
+            }
+        }
+        for (int j = 0; j < C::NMC; ++j, ++slot) {
+            float* sb = o + (int64_t)slot * C::SLOT;
+            for (int ml = 0; ml < C::MC; ++ml) {
+                const int m = h * C::NA + j * C::MC + ml;
+                if (m >= C::CMID) continue;
+                sb[C::OFF_B1 + ml] = f.b(n1)[m];
+                for (int t = 0; t < 9; ++t) sb[C::OFF_WD + ml * 9 + t] = f.w(nd)[m * 9 + t];
+                sb[C::OFF_BD + ml] = f.b(nd)[m];
+                for (int n = 0; n < C::COUT; ++n) put_kmajor_split(sb + C::OFF_W2, sb + C::OFF_W2 + C::COUTP * C::MC, n, ml, C::MC, f.w(n2)[n * C::CMID + m]);
+            }
+        }
+    }
+    for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
+    return off;
+}
+
 template <class C>
 int64_t pack_dwpwtc(std::vector<float>& out, const Folded& f, const std::string& nd, const std::string& n2) {
     pad4(out);
@@ -670,6 +722,16 @@ Group make_dwpwtc(const char* name, int out_ch) {
     g.name = name;
     g.launch = &launch_dwpwtc<C>;
     g.occupancy = &occ_dwpwtc<C>;
+    g.out_ch = out_ch;
+    return g;
+}
+
+template <class C>
+Group make_irbtc2(const char* name, int out_ch) {
+    Group g{};
+    g.name = name;
+    g.launch = &launch_irbtc2<C>;
+    g.occupancy = &occ_irbtc2<C>;
     g.out_ch = out_ch;
     return g;
 }
@@ -823,11 +885,11 @@ static void build_plan(yf_ctx* ctx) {
         g.a.skip = ctx->d_skip;
         chain(g, 16, 32);
     }
-    chain(make_irb<CfgRes5>("res5_1", 48), 32, 32);
-    chain(make_irb<CfgRes5>("res5_2", 48), 32, 32);
-    chain(make_irb<CfgRes5>("res5_3", 48), 32, 32);
-    chain(make_irb<CfgRes5>("res5_4", 48), 32, 32);
-    chain(make_irb<CfgRes5>("res5_5", 48), 32, 32);
+#if YF_USE_TC
+    for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"}) chain(make_irbtc2<CfgRes5Tc>(n, 48), 32, 32);
+#else
+    for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"}) chain(make_irb<CfgRes5>(n, 48), 32, 32);
+#endif
     { Group g{}; g.name = "conv5_2"; g.launch = &launch_pw52; g.out_ch = 96; chain(g, 32, 32); }
     const float* conv5_2 = prev;
 #if YF_USE_TC
@@ -900,7 +962,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         init_thin<CfgRes1Thin>(),
 #endif
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -975,7 +1037,12 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     res(CfgRes4{}, "res4_1"); res(CfgRes4{}, "res4_2"); res(CfgRes4{}, "res4_3"); res(CfgRes4{}, "res4_4");
 #endif
     offs.push_back(pack_irb<CfgDown4>(P, f, "conv4_2", "conv4_3", "conv5_1", "", 0));
+#if YF_USE_TC
+    for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"})
+        offs.push_back(pack_irbtc2<CfgRes5Tc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
+#else
     res(CfgRes5{}, "res5_1"); res(CfgRes5{}, "res5_2"); res(CfgRes5{}, "res5_3"); res(CfgRes5{}, "res5_4"); res(CfgRes5{}, "res5_5");
+#endif
     offs.push_back(pack_pw52(P, f));
 #if YF_USE_TC
     offs.push_back(pack_dwpwtc<CfgNeckS1Tc>(P, f, "conv5_3", "conv5_4"));
