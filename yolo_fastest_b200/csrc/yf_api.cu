@@ -295,6 +295,16 @@ using CfgNeckS1Tc = YF_CFGNECKS1_TC;
 #define YF_CFGNECKL1_TC DwPwTcCfg<96, 96, 5, 8, 40, 16, 4, 10, false>
 #endif
 using CfgNeckL1Tc = YF_CFGNECKL1_TC;
+// head groups with at most 32 output channels (the shipped 3-class models: 24): depthwise 5x5 -> composed 1x1, N = 32
+#ifndef YF_CFGNECKS2_TC
+#define YF_CFGNECKS2_TC DwPwTcCfg<128, 32, 5, 16, 20, 16, 4, 10, false, true>
+#endif
+using CfgNeckS2Tc = YF_CFGNECKS2_TC;
+#ifndef YF_CFGNECKL2_TC
+#define YF_CFGNECKL2_TC DwPwTcCfg<96, 32, 5, 8, 40, 16, 4, 10, false, true>
+#endif
+using CfgNeckL2Tc = YF_CFGNECKL2_TC;
+static bool heads_on_tc(int nout) { return YF_USE_TC && nout <= 32; }
 using CfgUpCatTc = UpCatTcCfg<10>;
 // widest residual blocks on the chunked tensor-core engine: IrbTc2Cfg<CIN, CMID, COUT, TH, TW, N halves, RH, worker warps, RES>
 #ifndef YF_CFGRES5_TC
@@ -351,7 +361,7 @@ void launch_dwpwtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;
-    dwpw_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+    dwpw_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total, g.headn > 0 ? g.headn : C::N);
 }
 template <class C> int occ_dwpwtc() { return occ_of(dwpw_tc_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
@@ -500,6 +510,35 @@ int64_t pack_thin(std::vector<float>& out, const Folded& f, const std::string& n
         for (int n = 0; n < C::COUT; ++n) wm[C::OFF_W2 + n] = f.w(n2)[n * C::CMID + m];
     }
     for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
+    return off;
+}
+
+// head group on the tensor-core depthwise -> 1x1 kernel: n2 (linear 1x1) and nh (biased head conv) composed as in pack_irb
+template <class C>
+int64_t pack_dwpwtc_head(std::vector<float>& out, const Folded& f, const std::string& nd, const std::string& n2, const std::string& nh, int mid, int headn) {
+    pad4(out);
+    while (out.size() % 32) out.push_back(0.f);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int c = 0; c < C::NCHUNK; ++c) {
+        float* cb = o + (int64_t)c * C::CB;
+        for (int ml = 0; ml < C::MC; ++ml) {
+            const int m = c * C::MC + ml;
+            for (int t = 0; t < C::KK; ++t) cb[C::OFF_WD + ml * C::KK + t] = f.w(nd)[m * C::KK + t];
+            cb[C::OFF_BD + ml] = f.b(nd)[m];
+            for (int n = 0; n < headn; ++n) {
+                double a = 0.0;
+                for (int k = 0; k < mid; ++k) a += (double)f.w(nh)[n * mid + k] * (double)f.w(n2)[k * C::C + m];
+                put_kmajor_split(cb + C::OFF_WH, cb + C::OFF_WL, n, ml, C::MC, (float)a);
+            }
+        }
+    }
+    for (int n = 0; n < headn; ++n) {
+        double b = (double)f.b(nh)[n];
+        for (int k = 0; k < mid; ++k) b += (double)f.w(nh)[n * mid + k] * (double)f.b(n2)[k];
+        o[C::OFF_B + n] = (float)b;
+    }
     return off;
 }
 
@@ -898,7 +937,7 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgNeckS1>("conv5_4", 128), 32, 32);
 #endif
     {
-        Group g = make_irb<CfgNeckS2>("head_5", 0);   // y = caller's head_small, set per call
+        Group g = heads_on_tc(ctx->nout) ? make_dwpwtc<CfgNeckS2Tc>("head_5", 0) : make_irb<CfgNeckS2>("head_5", 0);   // y = caller's head_small, set per call
         hw(g, 32, 32); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
     {
@@ -913,7 +952,7 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgNeckL1>("conv4_1_3", 96), 16, 16);
 #endif
     {
-        Group g = make_irb<CfgNeckL2>("head_4", 0);   // y = caller's head_large
+        Group g = heads_on_tc(ctx->nout) ? make_dwpwtc<CfgNeckL2Tc>("head_4", 0) : make_irb<CfgNeckL2>("head_4", 0);   // y = caller's head_large
         hw(g, 16, 16); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
 }
@@ -962,7 +1001,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         init_thin<CfgRes1Thin>(),
 #endif
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -1049,14 +1088,16 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
 #else
     offs.push_back(pack_irb<CfgNeckS1>(P, f, "", "conv5_3", "conv5_4", "", 0));
 #endif
-    offs.push_back(pack_irb<CfgNeckS2>(P, f, "", "conv5_5", "conv5_6", "head_5", ctx->nout));
+    offs.push_back(heads_on_tc(ctx->nout) ? pack_dwpwtc_head<CfgNeckS2Tc>(P, f, "conv5_5", "conv5_6", "head_5", 128, ctx->nout)
+                                          : pack_irb<CfgNeckS2>(P, f, "", "conv5_5", "conv5_6", "head_5", ctx->nout));
     offs.push_back(upcat_on_tc(ctx->H, ctx->W) ? pack_upcat_tc(P, f) : pack_upcat(P, f));
 #if YF_USE_TC
     offs.push_back(pack_dwpwtc<CfgNeckL1Tc>(P, f, "conv4_1_2", "conv4_1_3"));
 #else
     offs.push_back(pack_irb<CfgNeckL1>(P, f, "", "conv4_1_2", "conv4_1_3", "", 0));
 #endif
-    offs.push_back(pack_irb<CfgNeckL2>(P, f, "", "conv4_1_4", "conv4_1_5", "head_4", ctx->nout));
+    offs.push_back(heads_on_tc(ctx->nout) ? pack_dwpwtc_head<CfgNeckL2Tc>(P, f, "conv4_1_4", "conv4_1_5", "head_4", 96, ctx->nout)
+                                          : pack_irb<CfgNeckL2>(P, f, "", "conv4_1_4", "conv4_1_5", "head_4", ctx->nout));
     pad4(P);
     if (offs.size() != ctx->groups.size()) { set_err(&ctx->err, "internal: %zu packs vs %zu groups", offs.size(), ctx->groups.size()); return YF_ERR_STATE; }
     for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);      // graphs bake the weight pointers in

@@ -9,6 +9,8 @@
 // Same warp-specialised skeleton as yf_tc.cuh: NWW worker warps stage the input chunk (cp.async, double buffered), run the
 // depthwise and write its output as the split MMA operand (double buffered); one extra warp issues the MMAs and the weight-block
 // bulk copies (3-deep ring). The MMA of chunk q runs while the workers compute chunk q + 1.
+// The head groups (conv5_5 -> conv5_6 -> head_5, conv4_1_4 -> conv4_1_5 -> head_4) use the same kernel with the two 1x1s composed
+// into one [C][headn] matrix on the host (see yf_kernels.cuh, HEADC) when headn <= 32: N = 32 columns, `nout` = headn stored.
 // Packed weights (floats): NCHUNK x { [Whi: NP x MC K-major][Wlo][Wd: MC*KK][bd: MC] }, then [b: N].
 #pragma once
 #include "yf_tc.cuh"
@@ -19,10 +21,11 @@ __device__ __forceinline__ void cp_async8(float* dst, const float* src, int src_
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
 
-template <int C_, int N_, int KS_, int TH_, int TW_, int MC_, int RH_, int NWW_, bool RELU_>
+template <int C_, int N_, int KS_, int TH_, int TW_, int MC_, int RH_, int NWW_, bool RELU_, bool NRT_ = false>
 struct DwPwTcCfg {
     static constexpr int C = C_, N = N_, MC = MC_, RH = RH_, NWW = NWW_;
     static constexpr bool RELU = RELU_;
+    static constexpr bool NRT = NRT_;             // the number of stored output channels is a run-time argument (head groups)
     static constexpr int NTW = NWW * 32, NT = NTW + 32, NWB = 3;
     using G = Geo<KS_, 1, TH_, TW_>;
     static constexpr int KK = KS_ * KS_;
@@ -98,7 +101,7 @@ __device__ __forceinline__ void dwk_stage_split(int tid, const float* __restrict
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
 dwpw_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts, int H, int W,
-               int tiles_x, int tiles_y, int total_tiles) {
+               int tiles_x, int tiles_y, int total_tiles, int nout /* output channels actually stored, <= N (head groups: run time) */) {
     using G = typename C::G;
     constexpr int NTW = C::NTW, NWW = C::NWW, NCH = C::NCHUNK;
     extern __shared__ unsigned char smem_raw[];
@@ -250,10 +253,11 @@ dwpw_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float* 
                 float v[16];
                 tmem_ld16(tmem + lane_base + mt * C::NP + c0, v);
                 if (pix < G::OPIX && gy < H && gx < W) {
-                    float* yp = y + ((size_t)tb * C::N + c0) * plane + (size_t)gy * W + gx;
+                    const int nch = C::NRT ? nout : C::N;
+                    float* yp = y + ((size_t)tb * nch + c0) * plane + (size_t)gy * W + gx;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        if (c0 + i < C::N) {
+                        if (c0 + i < nch) {
                             float r = v[i] + __ldg(wts + C::OFF_B + c0 + i);
                             if (C::RELU) r = fmaxf(r, 0.f);
                             yp[i * plane] = r;
