@@ -19,6 +19,7 @@
 #include "yf_tcpw.cuh"
 #include "yf_tcup.cuh"
 #include "yf_tcirb2.cuh"
+#include "yf_tcdense.cuh"
 
 using namespace yf;
 
@@ -306,6 +307,7 @@ using CfgNeckS2Tc = YF_CFGNECKS2_TC;
 using CfgNeckL2Tc = YF_CFGNECKL2_TC;
 static bool heads_on_tc(int nout) { return YF_USE_TC && nout <= 32; }
 using CfgUpCatTc = UpCatTcCfg<10>;
+using CfgDenseTc = DenseTcCfg<12>;
 // widest residual blocks on the chunked tensor-core engine: IrbTc2Cfg<CIN, CMID, COUT, TH, TW, N halves, RH, worker warps, RES>
 #ifndef YF_CFGRES5_TC
 #define YF_CFGRES5_TC IrbTc2Cfg<48, 224, 48, 8, 20, 2, 2, 10, true>
@@ -402,6 +404,14 @@ void launch_stem(const GroupArgs& g, const void* xin, bool u8in, int B, cudaStre
     const int grid = total < g.resident ? total : g.resident;
     if (u8in) stem_kernel<C, true><<<grid, C::NT, C::SMEM_BYTES, st>>>(xin, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
     else stem_kernel<C, false><<<grid, C::NT, C::SMEM_BYTES, st>>>(xin, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
+}
+int occ_dense_tc() { return occ_of(dense_tc_kernel<CfgDenseTc>, CfgDenseTc::NT, CfgDenseTc::SMEM_BYTES); }
+void launch_dense_tc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using C = CfgDenseTc;
+    const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    dense_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
 }
 void launch_dense(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using C = CfgDense;
@@ -683,6 +693,28 @@ int64_t pack_stem(std::vector<float>& out, const Folded& f) {
     return off;
 }
 
+// dense_tc_kernel: 27 resident B operands (channel block cb, tap t): 64 rows x 8 input channels, rows 0..23 = hi, 32..55 = lo of W9
+int64_t pack_dense_tc(std::vector<float>& out, const Folded& f) {
+    using C = CfgDenseTc;
+    pad4(out);
+    while (out.size() % 32) out.push_back(0.f);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    const float* w9 = f.w("conv1_9");   // [24][24][3][3]
+    for (int cb = 0; cb < 3; ++cb)
+        for (int t = 0; t < 9; ++t) {
+            float* blk = o + (int64_t)(cb * 9 + t) * 512;
+            for (int n = 0; n < 24; ++n)
+                for (int kl = 0; kl < 8; ++kl) put_kmajor_split(blk, blk + 32 * 8, n, kl, 8, w9[((n * 24 + cb * 8 + kl) * 3 + t / 3) * 3 + t % 3]);
+        }
+    for (int i = 0; i < 96; ++i) o[C::OFF_W8 + i] = f.w("conv1_8")[i];          // [24][4]
+    for (int i = 0; i < 24; ++i) { o[C::OFF_B8 + i] = f.b("conv1_8")[i]; o[C::OFF_B9 + i] = f.b("conv1_9")[i]; }
+    for (int i = 0; i < 192; ++i) o[C::OFF_W21 + i] = f.w("conv2_1")[i];        // [8][24]
+    for (int i = 0; i < 8; ++i) o[C::OFF_B21 + i] = f.b("conv2_1")[i];
+    return off;
+}
+
 int64_t pack_dense(std::vector<float>& out, const Folded& f) {
     using C = CfgDense;
     pad4(out);
@@ -889,7 +921,11 @@ static void build_plan(yf_ctx* ctx) {
 #else
     chain(make_irb<CfgRes1>("res1_1", 4), 2, 2);
 #endif
+#if YF_USE_TC
+    { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense_tc; g.occupancy = &occ_dense_tc; g.out_ch = 8; chain(g, 2, 4); }
+#else
     { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense; g.occupancy = &occ_dense; g.out_ch = 8; chain(g, 2, 4); }
+#endif
     chain(make_irb<CfgRes2>("res2_1", 8), 4, 4);
     chain(make_irb<CfgRes2>("res2_2", 8), 4, 4);
     chain(make_irb<CfgDown2>("conv3_1", 8), 4, 8);
@@ -993,6 +1029,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         cudaFuncSetAttribute(stem_kernel<CfgStem, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem::SMEM_BYTES),
         cudaFuncSetAttribute(stem_kernel<CfgStem, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem::SMEM_BYTES),
         cudaFuncSetAttribute(dense_kernel<CfgDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDense::SMEM_BYTES),
+        cudaFuncSetAttribute(dense_tc_kernel<CfgDenseTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDenseTc::SMEM_BYTES),
         cudaFuncSetAttribute(pw_kernel<CfgPw52>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPw52::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_tc_kernel<CfgUpCatTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCatTc::SMEM_BYTES),
@@ -1057,7 +1094,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
 #else
     res(CfgRes1{}, "res1_1");
 #endif
-    offs.push_back(pack_dense(P, f));
+    offs.push_back(YF_USE_TC ? pack_dense_tc(P, f) : pack_dense(P, f));
     res(CfgRes2{}, "res2_1"); res(CfgRes2{}, "res2_2");
     offs.push_back(pack_irb<CfgDown2>(P, f, "conv2_2", "conv2_3", "conv3_1", "", 0));
     res(CfgRes3a{}, "res3_1"); res(CfgRes3a{}, "res3_2");
