@@ -308,6 +308,12 @@ using CfgNeckL2Tc = YF_CFGNECKL2_TC;
 static bool heads_on_tc(int nout) { return YF_USE_TC && nout <= 32; }
 using CfgUpCatTc = UpCatTcCfg<10>;
 using CfgDenseTc = DenseTcCfg<12>;
+#ifndef YF_DENSE_TC
+#define YF_DENSE_TC YF_USE_TC       // the dense 3x3 group on tcgen05
+#endif
+#ifndef YF_RES5_TC
+#define YF_RES5_TC YF_USE_TC        // res5_* on tcgen05
+#endif
 // widest residual blocks on the chunked tensor-core engine: IrbTc2Cfg<CIN, CMID, COUT, TH, TW, N halves, RH, worker warps, RES>
 #ifndef YF_CFGRES5_TC
 #define YF_CFGRES5_TC IrbTc2Cfg<48, 224, 48, 8, 20, 2, 2, 10, true>
@@ -502,7 +508,7 @@ inline void put_kmajor_split(float* hi, float* lo, int n, int k, int K, float w)
     const int idx = ((n >> 3) * (K / 4) + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
     const float h = tf32_rna_host(w);
     hi[idx] = h;
-    lo[idx] = w - h;
+    lo[idx] = tf32_rna_host(w - h);      // rounded, not left to the tensor core's truncation (which would bias every product the same way)
 }
 
 template <class C>
@@ -921,7 +927,7 @@ static void build_plan(yf_ctx* ctx) {
 #else
     chain(make_irb<CfgRes1>("res1_1", 4), 2, 2);
 #endif
-#if YF_USE_TC
+#if YF_DENSE_TC
     { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense_tc; g.occupancy = &occ_dense_tc; g.out_ch = 8; chain(g, 2, 4); }
 #else
     { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense; g.occupancy = &occ_dense; g.out_ch = 8; chain(g, 2, 4); }
@@ -960,7 +966,7 @@ static void build_plan(yf_ctx* ctx) {
         g.a.skip = ctx->d_skip;
         chain(g, 16, 32);
     }
-#if YF_USE_TC
+#if YF_RES5_TC
     for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"}) chain(make_irbtc2<CfgRes5Tc>(n, 48), 32, 32);
 #else
     for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"}) chain(make_irb<CfgRes5>(n, 48), 32, 32);
@@ -1094,7 +1100,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
 #else
     res(CfgRes1{}, "res1_1");
 #endif
-    offs.push_back(YF_USE_TC ? pack_dense_tc(P, f) : pack_dense(P, f));
+    offs.push_back(YF_DENSE_TC ? pack_dense_tc(P, f) : pack_dense(P, f));
     res(CfgRes2{}, "res2_1"); res(CfgRes2{}, "res2_2");
     offs.push_back(pack_irb<CfgDown2>(P, f, "conv2_2", "conv2_3", "conv3_1", "", 0));
     res(CfgRes3a{}, "res3_1"); res(CfgRes3a{}, "res3_2");
@@ -1113,7 +1119,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     res(CfgRes4{}, "res4_1"); res(CfgRes4{}, "res4_2"); res(CfgRes4{}, "res4_3"); res(CfgRes4{}, "res4_4");
 #endif
     offs.push_back(pack_irb<CfgDown4>(P, f, "conv4_2", "conv4_3", "conv5_1", "", 0));
-#if YF_USE_TC
+#if YF_RES5_TC
     for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"})
         offs.push_back(pack_irbtc2<CfgRes5Tc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
 #else

@@ -296,7 +296,9 @@ irbtc_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __
                         umma_tf32(tmem + C::TM_O + mt * 2 * C::COUTP, ddh + mo + (uint64_t)(kb * C::KB3 * 4 / 16), wb + (uint64_t)(kb * 16), IDESC3A, kb ? 1u : first);
 #pragma unroll
                     for (int kb = 0; kb < C::MC / 8; ++kb)
-                        umma_tf32(tmem + C::TM_O + mt * 2 * C::COUTP, ddl + mo + (uint64_t)(kb * C::KB3 * 4 / 16), wb + (uint64_t)(kb * 16), IDESC3B, 1u);
+                        // D_lo . W2hi joins the other correction term D_hi . W2lo in the second column group: the tensor core accumulates
+                        // with truncation, so the main term D_hi . W2hi gets the shortest possible accumulation chain
+                        umma_tf32(tmem + C::TM_O + mt * 2 * C::COUTP + C::COUTP, ddl + mo + (uint64_t)(kb * C::KB3 * 4 / 16), wb + (uint64_t)(kb * 16), IDESC3B, 1u);
                 }
                 umma_commit(&dfree);
             };

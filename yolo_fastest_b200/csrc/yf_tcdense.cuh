@@ -15,6 +15,10 @@
 #pragma once
 #include "yf_tcpw.cuh"
 
+#ifndef YF_DSPLIT
+#define YF_DSPLIT 1      // 1: one accumulator per channel block (hi.hi chains of 9 MMAs), 0: one per tile (chains of 27)
+#endif
+
 namespace yf {
 
 template <int NWW_>
@@ -28,7 +32,7 @@ struct DenseTcCfg {
     static constexpr int WRES = 27 * 64 * 8;                                        // resident B operands
     static constexpr int OFF_W8 = WRES, OFF_B8 = OFF_W8 + 96, OFF_B9 = OFF_B8 + 24, OFF_W21 = OFF_B9 + 24, OFF_B21 = OFF_W21 + 192;   // all multiples of 4
     static constexpr int WFLOATS = rup(OFF_B21 + 8, 4);
-    static constexpr int TCOLS = 128;                                               // 2 accumulator buffers x 64 columns
+    static constexpr int TCOLS = 512;                                               // 2 tile buffers x 3 channel-block accumulators x 64 columns
     static constexpr int WPAD = rup(WFLOATS, 32);
     static constexpr int SMEM_FLOATS = 4 * DA1 + WPAD + 2 * XS1;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + 1024;
@@ -87,8 +91,11 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const uint64_t wb = dw0 + (uint64_t)(((cb * 9 + t) * 512 * 4) >> 4);
-                        umma_tf32(tmem + ob * 64, db + (uint64_t)(t * C::KBLK * 4 / 16), wb, IDESC_A, (cb | t) ? 1u : 0u);
-                        umma_tf32(tmem + ob * 64, db + (uint64_t)((C::DA1 + t * C::KBLK) * 4 / 16), wb, IDESC_B, 1u);
+                        // one accumulator per channel block: the tensor core accumulates with truncation, so the rounding bias grows
+                        // with the length of an accumulation chain — 18 MMAs here instead of 54; the epilogue adds the three in fp32
+                        umma_tf32(tmem + ob * 192 + YF_DSPLIT * cb * 64, db + (uint64_t)(t * C::KBLK * 4 / 16), wb, IDESC_A, (t | ((1 - YF_DSPLIT) * cb)) ? 1u : 0u);
+                        // the lo . hi correction joins the hi . lo correction (columns 32..63): the main term hi . hi keeps the shortest chain
+                        umma_tf32(tmem + ob * 192 + YF_DSPLIT * cb * 64 + 32, db + (uint64_t)((C::DA1 + t * C::KBLK) * 4 / 16), wb, IDESC_B, 1u);
                     }
                     umma_commit(&dfree[b]);
                 }
@@ -148,17 +155,24 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
             const int ob = te & 1;
             mbar_wait(&ofull[ob], (te >> 1) & 1);
             tc_fence_after();
-            const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ob * 64;
-            float a0[16], a1[8], l0[16], l1[8];
-            tmem_ld16(ta, a0); tmem_ld8(ta + 16, a1); tmem_ld16(ta + 32, l0); tmem_ld8(ta + 48, l1);
+            const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ob * 192;
+            float v[24];
+#pragma unroll
+            for (int n = 0; n < 24; ++n) v[n] = Wr[C::OFF_B9 + n];
+#pragma unroll
+            for (int cb = 0; cb < (YF_DSPLIT ? 3 : 1); ++cb) {
+                float a0[16], a1[8], l0[16], l1[8];
+                tmem_ld16(ta + cb * 64, a0); tmem_ld8(ta + cb * 64 + 16, a1); tmem_ld16(ta + cb * 64 + 32, l0); tmem_ld8(ta + cb * 64 + 48, l1);
+#pragma unroll
+                for (int n = 0; n < 16; ++n) v[n] += a0[n] + l0[n];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) v[16 + n] += a1[n] + l1[n];
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ofree[ob]);
-            float v[24];
 #pragma unroll
-            for (int n = 0; n < 16; ++n) v[n] = fmaxf(a0[n] + l0[n] + Wr[C::OFF_B9 + n], 0.f);
-#pragma unroll
-            for (int n = 0; n < 8; ++n) v[16 + n] = fmaxf(a1[n] + l1[n] + Wr[C::OFF_B9 + 16 + n], 0.f);
+            for (int n = 0; n < 24; ++n) v[n] = fmaxf(v[n], 0.f);
             const int gy = ey0 + oyl, gx = ex0 + oxl;                // this thread's pixel m (every kx group holds all 128 pixels)
             if (gy < Hout && gx < Wout) {
 #pragma unroll
