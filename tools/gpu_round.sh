@@ -17,7 +17,7 @@ timeout 600 python bench.py --batch 1 --steps 200 --warmup 20 --no-cpu-baseline 
 echo "bench b1 exit $?" >> gpurun_out/summary.txt
 # every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
-  timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"irb_kernel|irbtc_kernel|dwpw_tc_kernel|dense_kernel|stem_kernel|upcat_kernel|pw_kernel|post_kernel" -c 400 --csv --log-file gpurun_out/launches.csv \
+  timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"irb_kernel|irbtc_kernel|irbtc2_kernel|dwpw_tc_kernel|dense_kernel|dense_tc_kernel|stem_kernel|upcat_kernel|upcat_tc_kernel|pw_kernel|post_kernel" -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt

@@ -3,40 +3,49 @@
 //
 //   O9[out px][n] = sum over taps t = (ky, kx) and channels c of  E[c][2 oy + ky - 1][2 ox + kx - 1] . W9[n][c][ky][kx]       K = 9 x 24 = 216
 //
-// A tile is 8 x 16 output pixels = exactly one 128-row MMA tile. The A operand is written tap by tap by the worker threads (im2col in
-// shared memory): thread = (output pixel, kx); for each ky it reads the 4 input channels of its input pixel from the staged x tile,
-// evaluates conv1_8 for the 8 channels of the current channel block (4 FMAs each — cheaper than staging E and copying it: an
-// MN-major swizzled operand cannot be a shifted window of another array), splits the result into hi/lo (3xTF32) and stores it at
-// its pixel's row of the operand block of tap t. One step = one channel block = 9 taps x 8 channels = 9 K-blocks (72 KB with hi and
-// lo; double buffered); per step the tensor-core thread issues 9 x { D_hi . [W9hi | W9lo] (N = 64), D_lo . W9hi (N = 32) }; all
-// 27 weight blocks (55 KB) are resident. The accumulators are double buffered in TMEM, so the epilogue of tile t (thread = pixel:
-// sum of the two column groups + b9, ReLU, then conv2_1 as 192 FMAs in registers, 8 channel stores) overlaps the MMAs of tile t + 1.
+// No im2col: the A operand of every tap is a SHIFTED WINDOW of one array. E = relu(conv1_8(x)) is computed once per input pixel
+// and stored (hi and lo parts, 3xTF32) as [4-channel group][column parity][input row][column / 2][4 channels]. That is the K-major,
+// un-swizzled operand layout: a core matrix = 8 consecutive pixels x 16 bytes (4 channels), the K-adjacent core matrix one
+// channel-group plane pair further (LBO), the next 8-pixel row group TWO input rows further (SBO) — so with a tile of 16 x 8 output
+// pixels (row group = one output row) the operand of tap (ky, kx) is the same array read from start address
+// base + parity(kx) plane + ky rows + (kx >> 1) pixels: the descriptor's 16-byte start granularity is exactly one pixel.
+// (An MN-major swizzled operand, as used by the other kernels, cannot start at an odd pixel; the first version of this kernel
+// therefore copied every tap into its own operand block — 2.25 stores per E value, 21 k instructions per tile — and was worker-bound.)
+//
+// One step = one block of 8 channels (2 channel groups) of E for the whole input tile, 3 steps per tile, 3-deep ring; per step the
+// tensor-core thread issues 9 taps x { E_hi . [W9hi | W9lo] (N = 64), E_lo . W9hi (N = 32, into the correction columns) } into
+// the step's own accumulator (chains of 9 MMAs: the tensor core accumulates with truncation); all 27 weight blocks (55 KB) are
+// resident. The accumulators of a tile are double buffered in TMEM, so the epilogue of tile t (thread = pixel: sum of the three
+// accumulators + b9, ReLU, then conv2_1 as FMAs in registers) runs one step late and overlaps the MMAs of tile t + 1.
 // Packed weights (floats): [27 x (64 x 8 K-major): rows 0..23 W9hi, 32..55 W9lo][w8: 24 x 4][b8: 24][b9: 24][w21: 8 x 24][b21: 8].
 #pragma once
 #include "yf_tcpw.cuh"
-
-#ifndef YF_DSPLIT
-#define YF_DSPLIT 1      // 1: one accumulator per channel block (hi.hi chains of 9 MMAs), 0: one per tile (chains of 27)
-#endif
 
 namespace yf {
 
 template <int NWW_>
 struct DenseTcCfg {
     static constexpr int NWW = NWW_, NTW = NWW * 32, NT = NTW + 32;
-    static constexpr int TH = 8, TW = 16, OPIX = TH * TW;
-    static constexpr int RH = 2 * TH + 1, RWP = TW + 1, XW = 36;                     // staged x tile [4][RH][XW]: RWP column PAIRS from column 2 ox0 - 2
+    static constexpr int TH = 16, TW = 8, OPIX = TH * TW;
+    static constexpr int RH = 2 * TH + 1, RW = 2 * TW + 1;                          // input rows / columns feeding a tile
+    static constexpr int XWP = TW + 1, XW = 2 * XWP + 2;                            // staged x tile [4][RH][XW]: XWP column pairs from column 2 ox0 - 2
     static constexpr int XS1 = rup(4 * RH * XW, 32);
-    static constexpr int KBLK = 4 * 256;                                            // floats of one K-block (8 channels x 128 pixels)
-    static constexpr int DA1 = 9 * KBLK;                                            // one operand chunk (hi or lo): 9 taps
+    static constexpr int XH = TW + 1;                                               // E entries per row and parity (even columns: TW + 1, odd: TW)
+    static constexpr int ROW = XH * 4;                                              // floats per E row
+    static constexpr int PLANE = rup(RH * ROW, 32) + 16;                            // floats per (channel group, parity) plane; 64 B mod 128 B, so the
+                                                                                    // two parities of a warp's 128-bit stores fall on different banks
+    static constexpr int HL = 4 * PLANE;                                            // hi (or lo) part of a slot: 2 channel groups x 2 parities
+    static constexpr int SLOT = 2 * HL, NS = 3;                                     // ring of 3 slots
     static constexpr int WRES = 27 * 64 * 8;                                        // resident B operands
     static constexpr int OFF_W8 = WRES, OFF_B8 = OFF_W8 + 96, OFF_B9 = OFF_B8 + 24, OFF_W21 = OFF_B9 + 24, OFF_B21 = OFF_W21 + 192;   // all multiples of 4
     static constexpr int WFLOATS = rup(OFF_B21 + 8, 4);
-    static constexpr int TCOLS = 512;                                               // 2 tile buffers x 3 channel-block accumulators x 64 columns
     static constexpr int WPAD = rup(WFLOATS, 32);
-    static constexpr int SMEM_FLOATS = 4 * DA1 + WPAD + 2 * XS1;
+    static constexpr int TCOLS = 512;                                               // 2 tile buffers x 3 step accumulators x 64 columns
+    static constexpr int NPIX_IN = RH * RW;
+    static constexpr int NITEM = 2 * NPIX_IN, IPT = cdiv(NITEM, NTW);               // producer items (input pixel, channel group) per step / per thread
+    static constexpr int SMEM_FLOATS = NS * SLOT + WPAD + 2 * XS1;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + 1024;
-    static_assert(NTW == 3 * OPIX, "one worker thread per (output pixel, kx)");
+    static_assert(NTW >= 3 * OPIX && (PLANE * 4) % 128 == 64, "epilogue mapping / bank layout");
     static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
 };
 
@@ -47,16 +56,17 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
     constexpr int NTW = C::NTW, NWW = C::NWW;
     extern __shared__ unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-    float* Dbuf = base;                          // [2 buffers][hi | lo][9 taps][8 ch x 128 px]
-    float* Wr = Dbuf + 4 * C::DA1;               // resident weights
-    float* Xs0 = Wr + C::WPAD;                    // [2 buffers][4][RH][XW]
-    __shared__ __align__(8) uint64_t wres, dfull[2], dfree[2], ofull[2], ofree[2];
+    float* Ebuf = base;                          // [NS slots][hi | lo][2 channel groups][2 parities][RH][XH][4]
+    float* Wr = Ebuf + C::NS * C::SLOT;          // resident weights
+    float* Xs0 = Wr + C::WPAD;                   // [2 buffers][4][RH][XW]
+    __shared__ __align__(8) uint64_t wres, dfull[C::NS], dfree[C::NS], ofull[2], ofree[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         mbar_init(&wres, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], NWW); mbar_init(&dfree[i], 1); mbar_init(&ofull[i], 1); mbar_init(&ofree[i], NWW); }
+        for (int i = 0; i < C::NS; ++i) { mbar_init(&dfull[i], NWW); mbar_init(&dfree[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&ofull[i], 1); mbar_init(&ofree[i], NWW); }
         mbar_fence_init();
     }
     if (warp == NWW) {
@@ -72,40 +82,40 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
     if (warp == NWW) {
         // ================= tensor-core warp =================
         if (lane == 0 && ntile > 0) {
-            constexpr uint32_t IDESC_A = umma_idesc_tf32(64), IDESC_B = umma_idesc_tf32(32);
+            // instruction descriptors: A is K-major here (bit 15 clear), unlike the MN-major operands of the other kernels
+            constexpr uint32_t IDESC_A = umma_idesc_tf32(64) & ~(1u << 15), IDESC_B = umma_idesc_tf32(32) & ~(1u << 15);
             mbar_expect_tx(&wres, C::WFLOATS * 4);
             bulk_load(Wr, wts, C::WFLOATS * 4, &wres);
-            const uint64_t dd0 = umma_desc(smem_u32(Dbuf), 1024, 512, 1);
+            // A: core matrices of 8 pixels x 16 B; K-adjacent one = next channel group (2 planes further, LBO), next row group = two input rows (SBO)
+            const uint64_t de0 = umma_desc(smem_u32(Ebuf), 2 * C::PLANE * 4, 2 * C::ROW * 4, 0);
             const uint64_t dw0 = umma_desc(smem_u32(Wr), 128, 256, 0);
             mbar_wait(&wres, 0);
             int d = 0;
             for (int ti = 0; ti < ntile; ++ti) {
                 const int ob = ti & 1;
-                if (ti >= 2) mbar_wait(&ofree[ob], ((ti >> 1) - 1) & 1);       // the tile that used this accumulator buffer has been read out
+                if (ti >= 2) mbar_wait(&ofree[ob], ((ti >> 1) - 1) & 1);       // the tile that used these accumulators has been read out
 #pragma unroll 1
                 for (int cb = 0; cb < 3; ++cb, ++d) {
-                    const int b = d & 1;
-                    mbar_wait(&dfull[b], (d >> 1) & 1);
+                    const int sl = d % C::NS;
+                    mbar_wait(&dfull[sl], (d / C::NS) & 1);
                     tc_fence_after();
-                    const uint64_t db = dd0 + (uint64_t)((uint32_t)(b * 2 * C::DA1 * 4) >> 4);
+                    const uint64_t db = de0 + (uint64_t)(((uint32_t)sl * C::SLOT * 4) >> 4);
+                    const uint32_t acc = tmem + ob * 192 + cb * 64;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
+                        const int ky = t / 3, kx = t % 3;
                         const uint64_t wb = dw0 + (uint64_t)(((cb * 9 + t) * 512 * 4) >> 4);
-                        // one accumulator per channel block: the tensor core accumulates with truncation, so the rounding bias grows
-                        // with the length of an accumulation chain — 18 MMAs here instead of 54; the epilogue adds the three in fp32
-                        umma_tf32(tmem + ob * 192 + YF_DSPLIT * cb * 64, db + (uint64_t)(t * C::KBLK * 4 / 16), wb, IDESC_A, (t | ((1 - YF_DSPLIT) * cb)) ? 1u : 0u);
-                        // the lo . hi correction joins the hi . lo correction (columns 32..63): the main term hi . hi keeps the shortest chain
-                        umma_tf32(tmem + ob * 192 + YF_DSPLIT * cb * 64 + 32, db + (uint64_t)((C::DA1 + t * C::KBLK) * 4 / 16), wb, IDESC_B, 1u);
+                        const uint64_t ao = (uint64_t)((((kx & 1) * C::PLANE + ky * C::ROW + (kx >> 1) * 4) * 4) >> 4);
+                        umma_tf32(acc, db + ao, wb, IDESC_A, t ? 1u : 0u);                                   // E_hi . [W9hi | W9lo]
+                        umma_tf32(acc + 32, db + ao + (uint64_t)((C::HL * 4) >> 4), wb, IDESC_B, 1u);         // E_lo . W9hi -> correction columns
                     }
-                    umma_commit(&dfree[b]);
+                    umma_commit(&dfree[sl]);
                 }
                 umma_commit(&ofull[ob]);
             }
         }
     } else {
-        // ================= worker warps: thread = (output pixel m, kx) =================
-        const int m = tid % C::OPIX, kx = tid / C::OPIX;
-        const int oyl = m / C::TW, oxl = m - oyl * C::TW;
+        // ================= worker warps =================
         const int tpi = tiles_x * tiles_y;
         const uint32_t inv_tx = (65536u + (uint32_t)tiles_x - 1u) / (uint32_t)tiles_x;
         auto origin = [&](int ti, int& b, int& oy0, int& ox0) {
@@ -116,25 +126,25 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
             oy0 = ty * C::TH; ox0 = (t - ty * tiles_x) * C::TW;
         };
         const size_t plane = (size_t)Hin * Win;
-        // x tile [4][RH][2 RWP] of image b at input rows 2 oy0 - 1 .., columns 2 ox0 - 2 .. -> dst, zero outside the image (8-byte cp.async)
+        // x tile [4][RH][2 XWP] of image b at input rows 2 oy0 - 1 .., columns 2 ox0 - 2 .. -> dst, zero outside the image (8-byte cp.async)
         auto stage_x = [&](int b, int oy0, int ox0, float* dst) {
             const float* src = x + (size_t)b * 4 * plane;
             const bool even = (Win & 1) == 0;                        // column pairs never straddle the image edge
-            for (int idx = tid; idx < 4 * C::RH * C::RWP; idx += NTW) {
-                const int k = idx / (C::RH * C::RWP), rem = idx - k * (C::RH * C::RWP);
-                const int r = rem / C::RWP, jp = rem - r * C::RWP;
+            for (int idx = tid; idx < 4 * C::RH * C::XWP; idx += NTW) {
+                const int k = idx / (C::RH * C::XWP), rem = idx - k * (C::RH * C::XWP);
+                const int r = rem / C::XWP, jp = rem - r * C::XWP;
                 const int gy = 2 * oy0 - 1 + r, gx = 2 * ox0 - 2 + 2 * jp;
                 const bool rowok = (unsigned)gy < (unsigned)Hin;
-                float* d = dst + (k * C::RH + r) * C::XW + 2 * jp;
+                float* dd = dst + (k * C::RH + r) * C::XW + 2 * jp;
                 const float* sp = src + (size_t)k * plane + (size_t)(rowok ? gy : 0) * Win;
                 if (even) {
                     const bool ok = rowok && (unsigned)gx < (unsigned)Win;
-                    cp_async8(d, ok ? sp + gx : src, ok ? 8 : 0);
+                    cp_async8(dd, ok ? sp + gx : src, ok ? 8 : 0);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const bool ok = rowok && (unsigned)(gx + e) < (unsigned)Win;
-                        cp_async4(d + e, ok ? sp + gx + e : src, ok ? 4 : 0);
+                        cp_async4(dd + e, ok ? sp + gx + e : src, ok ? 4 : 0);
                     }
                 }
             }
@@ -146,38 +156,53 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
             stage_x(nb, noy0, nox0, Xs0);
         }
         mbar_wait(&wres, 0);                                         // conv1_8 / bias / conv2_1 weights live behind the B operands
-        // this thread's operand address pieces: pixel row m inside a K-block
-        const int obase = (m >> 5) * 256 + (m & 7), mcx = (m & 31) >> 3;
-        // epilogue of tile te (thread = pixel; the three warps that share a TMEM lane quarter split the 8 output channels):
-        // O9 -> + b9, ReLU -> conv2_1 (24 -> 8) in registers -> HBM. Runs one step late (after the first step of the next tile), so the
-        // tensor core never waits for it and the workers never wait for the last MMAs of a tile.
+        // this thread's producer items (fixed for the whole kernel): item = cg * NPIX_IN + input pixel (r, j) -> E entry (cg, parity j & 1, r, j >> 1)
+        int it_x[C::IPT], it_e[C::IPT], it_rj[C::IPT];
+#pragma unroll
+        for (int i = 0; i < C::IPT; ++i) {
+            const int item = min(tid + i * NTW, C::NITEM - 1);
+            const int cg = item / C::NPIX_IN, pi = item - cg * C::NPIX_IN;
+            const int r = pi / C::RW, j = pi - r * C::RW;
+            it_rj[i] = r | (j << 8) | (cg << 16);
+            it_x[i] = r * C::XW + j + 1;                             // staged column index: the tile's column j sits at j + 1
+            it_e[i] = (cg * 2 + (j & 1)) * C::PLANE + r * C::ROW + (j >> 1) * 4;
+        }
+        // epilogue of tile te (thread = pixel; the three warps that share a TMEM lane quarter split the 8 output channels): the three
+        // step accumulators -> + b9, ReLU -> conv2_1 (24 -> 8) in registers -> HBM. Runs one step late (after the first step of the next
+        // tile), so the tensor core never waits for it and the workers never wait for the last MMAs of a tile.
+        const int em = (warp & 3) * 32 + lane, eoy = em >> 3, eox = em & 7, eg = warp >> 2;
         auto epilogue = [&](int te, int eb, int ey0, int ex0) {
             const int ob = te & 1;
-            mbar_wait(&ofull[ob], (te >> 1) & 1);
-            tc_fence_after();
-            const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ob * 192;
-            float v[24];
-#pragma unroll
-            for (int n = 0; n < 24; ++n) v[n] = Wr[C::OFF_B9 + n];
-#pragma unroll
-            for (int cb = 0; cb < (YF_DSPLIT ? 3 : 1); ++cb) {
-                float a0[16], a1[8], l0[16], l1[8];
-                tmem_ld16(ta + cb * 64, a0); tmem_ld8(ta + cb * 64 + 16, a1); tmem_ld16(ta + cb * 64 + 32, l0); tmem_ld8(ta + cb * 64 + 48, l1);
-#pragma unroll
-                for (int n = 0; n < 16; ++n) v[n] += a0[n] + l0[n];
-#pragma unroll
-                for (int n = 0; n < 8; ++n) v[16 + n] += a1[n] + l1[n];
+            if (eg < 3) {
+                mbar_wait(&ofull[ob], (te >> 1) & 1);
+                tc_fence_after();
             }
-            tc_fence_before();
+            float v[24];
+            if (eg < 3) {
+                const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ob * 192;
+#pragma unroll
+                for (int n = 0; n < 24; ++n) v[n] = Wr[C::OFF_B9 + n];
+#pragma unroll
+                for (int cb = 0; cb < 3; ++cb) {
+                    float a0[16], a1[8], l0[16], l1[8];
+                    tmem_ld16(ta + cb * 64, a0); tmem_ld8(ta + cb * 64 + 16, a1); tmem_ld16(ta + cb * 64 + 32, l0); tmem_ld8(ta + cb * 64 + 48, l1);
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) v[n] += a0[n] + l0[n];
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) v[16 + n] += a1[n] + l1[n];
+                }
+                tc_fence_before();
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ofree[ob]);
+            if (eg >= 3) return;
 #pragma unroll
             for (int n = 0; n < 24; ++n) v[n] = fmaxf(v[n], 0.f);
-            const int gy = ey0 + oyl, gx = ex0 + oxl;                // this thread's pixel m (every kx group holds all 128 pixels)
+            const int gy = ey0 + eoy, gx = ex0 + eox;
             if (gy < Hout && gx < Wout) {
 #pragma unroll
                 for (int jj = 0; jj < 3; ++jj) {
-                    const int j = kx * 3 + jj;                       // channels {0,1,2}, {3,4,5}, {6,7}
+                    const int j = eg * 3 + jj;                       // channels {0,1,2}, {3,4,5}, {6,7}
                     if (j < 8) {
                         float r = Wr[C::OFF_B21 + j];
 #pragma unroll
@@ -201,46 +226,43 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
             cp_async_wait_all();
             named_bar_sync<1, NTW>();                                // this tile's x has landed for everyone; the other buffer is free
             if (have_next) stage_x(nb, noy0, nox0, Xs0 + ((ti + 1) & 1) * C::XS1);
-            // the three input pixels (ky = 0..2) of this thread: tile coordinates (2 oyl + ky, 2 oxl + kx)
-            float xv[3][4];
-            bool in[3];
+            // this thread's input pixels: the 4 input channels and whether the pixel lies inside the image
+            float xv[C::IPT][4];
+            bool in[C::IPT];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int r = 2 * oyl + ky, j = 2 * oxl + kx;
-                in[ky] = (unsigned)(2 * oy0 - 1 + r) < (unsigned)Hin && (unsigned)(2 * ox0 - 1 + j) < (unsigned)Win;
+            for (int i = 0; i < C::IPT; ++i) {
+                in[i] = (unsigned)(2 * oy0 - 1 + (it_rj[i] & 255)) < (unsigned)Hin && (unsigned)(2 * ox0 - 1 + ((it_rj[i] >> 8) & 255)) < (unsigned)Win;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) xv[ky][k] = Xs[(k * C::RH + r) * C::XW + j + 1];
+                for (int k = 0; k < 4; ++k) xv[i][k] = Xs[k * C::RH * C::XW + it_x[i]];
             }
 #pragma unroll 1
             for (int cb = 0; cb < 3; ++cb, ++d) {
-                const int b = d & 1;
-                float4 w8r[8];
-                float b8r[8];
+                const int sl = d % C::NS;
+                if (d >= C::NS) mbar_wait(&dfree[sl], ((d / C::NS) - 1) & 1);
+                float* Eh = Ebuf + sl * C::SLOT;
 #pragma unroll
-                for (int cl = 0; cl < 8; ++cl) { w8r[cl] = ld4(Wr + C::OFF_W8 + (cb * 8 + cl) * 4); b8r[cl] = Wr[C::OFF_B8 + cb * 8 + cl]; }
-                if (d >= 2) mbar_wait(&dfree[b], ((d >> 1) - 1) & 1);
-                float* Dh = Dbuf + b * 2 * C::DA1;
+                for (int i = 0; i < C::IPT; ++i) {
+                    if (tid + i * NTW < C::NITEM) {
+                        const int c0 = cb * 8 + (it_rj[i] >> 16) * 4;  // first of this item's 4 channels
+                        float hi[4], lo[4];
 #pragma unroll
-                for (int cl = 0; cl < 8; ++cl) {
-                    const float4 w = w8r[cl];
-                    const float bb = b8r[cl];
-                    const int oc = obase + ((cl >> 2) & 1) * 128 + (cl & 3) * 32 + ((mcx ^ (cl & 3)) << 3);
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        float e = fmaf(w.x, xv[ky][0], bb);
-                        e = fmaf(w.y, xv[ky][1], e);
-                        e = fmaf(w.z, xv[ky][2], e);
-                        e = fmaf(w.w, xv[ky][3], e);
-                        e = in[ky] ? fmaxf(e, 0.f) : 0.f;            // conv1_9 zero-pads ITS input, the activation
-                        const float hi = tf32_hi(e);
-                        const int o = (ky * 3 + kx) * C::KBLK + oc;
-                        Dh[o] = hi;
-                        Dh[C::DA1 + o] = e - hi;
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const float4 w = ld4(Wr + C::OFF_W8 + (c0 + cc) * 4);
+                            float e = fmaf(w.x, xv[i][0], Wr[C::OFF_B8 + c0 + cc]);
+                            e = fmaf(w.y, xv[i][1], e);
+                            e = fmaf(w.z, xv[i][2], e);
+                            e = fmaf(w.w, xv[i][3], e);
+                            e = in[i] ? fmaxf(e, 0.f) : 0.f;          // conv1_9 zero-pads ITS input, the activation
+                            hi[cc] = tf32_hi(e);
+                            lo[cc] = e - hi[cc];
+                        }
+                        st4(Eh + it_e[i], make_float4(hi[0], hi[1], hi[2], hi[3]));
+                        st4(Eh + C::HL + it_e[i], make_float4(lo[0], lo[1], lo[2], lo[3]));
                     }
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&dfull[b]);
+                if (lane == 0) mbar_arrive(&dfull[sl]);
                 if (cb == 0 && ti > 0) epilogue(ti - 1, pb, poy0, pox0);
             }
         }
