@@ -716,7 +716,8 @@ int64_t pack_dense_tc(std::vector<float>& out, const Folded& f) {
         }
     for (int i = 0; i < 96; ++i) o[C::OFF_W8 + i] = f.w("conv1_8")[i];          // [24][4]
     for (int i = 0; i < 24; ++i) { o[C::OFF_B8 + i] = f.b("conv1_8")[i]; o[C::OFF_B9 + i] = f.b("conv1_9")[i]; }
-    for (int i = 0; i < 192; ++i) o[C::OFF_W21 + i] = f.w("conv2_1")[i];        // [8][24]
+    for (int j = 0; j < 8; ++j)
+        for (int n = 0; n < 24; ++n) o[C::OFF_W21 + n * 8 + j] = f.w("conv2_1")[j * 24 + n];        // [8][24] -> transposed [24][8]
     for (int i = 0; i < 8; ++i) o[C::OFF_B21 + i] = f.b("conv2_1")[i];
     return off;
 }

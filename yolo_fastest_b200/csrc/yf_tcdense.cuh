@@ -17,15 +17,23 @@
 // the step's own accumulator (chains of 9 MMAs: the tensor core accumulates with truncation); all 27 weight blocks (55 KB) are
 // resident. The accumulators of a tile are double buffered in TMEM, so the epilogue of tile t (thread = pixel: sum of the three
 // accumulators + b9, ReLU, then conv2_1 as FMAs in registers) runs one step late and overlaps the MMAs of tile t + 1.
-// Packed weights (floats): [27 x (64 x 8 K-major): rows 0..23 W9hi, 32..55 W9lo][w8: 24 x 4][b8: 24][b9: 24][w21: 8 x 24][b21: 8].
+// Packed weights (floats): [27 x (64 x 8 K-major): rows 0..23 W9hi, 32..55 W9lo][w8: 24 x 4][b8: 24][b9: 24][w21 transposed: 24 x 8][b21: 8].
 #pragma once
 #include "yf_tcpw.cuh"
 
 namespace yf {
 
+#if defined(YF_TC_TRACE) && defined(YF_DENSE_TRACE)
+#define DTRACE(tile, ev) do { if (blockIdx.x == 0 && (tile) < 64) g_tc_trace[(tile) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define DTRACE(tile, ev) do { } while (0)
+#endif
+
 template <int NWW_>
 struct DenseTcCfg {
-    static constexpr int NWW = NWW_, NTW = NWW * 32, NT = NTW + 32;
+    static constexpr int NWW = NWW_, NTW = NWW * 32;                                // producer warps / threads
+    static constexpr int NEW = 4;                                                   // epilogue warps (one per TMEM lane quarter)
+    static constexpr int NT = NTW + NEW * 32 + 32;                                  // + the tensor-core warp
     static constexpr int TH = 16, TW = 8, OPIX = TH * TW;
     static constexpr int RH = 2 * TH + 1, RW = 2 * TW + 1;                          // input rows / columns feeding a tile
     static constexpr int XWP = TW + 1, XW = 2 * XWP + 2;                            // staged x tile [4][RH][XW]: XWP column pairs from column 2 ox0 - 2
@@ -40,12 +48,13 @@ struct DenseTcCfg {
     static constexpr int OFF_W8 = WRES, OFF_B8 = OFF_W8 + 96, OFF_B9 = OFF_B8 + 24, OFF_W21 = OFF_B9 + 24, OFF_B21 = OFF_W21 + 192;   // all multiples of 4
     static constexpr int WFLOATS = rup(OFF_B21 + 8, 4);
     static constexpr int WPAD = rup(WFLOATS, 32);
-    static constexpr int TCOLS = 512;                                               // 2 tile buffers x 3 step accumulators x 64 columns
+    static constexpr int TCOLS = 512;                                               // 2 tile buffers x (3 step accumulators x 64 + 32 correction columns)
     static constexpr int NPIX_IN = RH * RW;
-    static constexpr int NITEM = 2 * NPIX_IN, IPT = cdiv(NITEM, NTW);               // producer items (input pixel, channel group) per step / per thread
+    static constexpr int NTH = NTW / 2, IPT = cdiv(NPIX_IN, NTH);                   // half of the workers per channel group; input pixels per thread and step
+    static constexpr int NSTG = 4 * RH * XWP, SPT = cdiv(NSTG, NTW);                // x-tile staging copies (8 bytes each) per tile / per producer thread
     static constexpr int SMEM_FLOATS = NS * SLOT + WPAD + 2 * XS1;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + 1024;
-    static_assert(NTW >= 3 * OPIX && (PLANE * 4) % 128 == 64, "epilogue mapping / bank layout");
+    static_assert(NEW * 32 == OPIX && (PLANE * 4) % 128 == 64, "epilogue mapping / bank layout");
     static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
 };
 
@@ -66,10 +75,10 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
     if (tid == 0) {
         mbar_init(&wres, 1);
         for (int i = 0; i < C::NS; ++i) { mbar_init(&dfull[i], NWW); mbar_init(&dfree[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&ofull[i], 1); mbar_init(&ofree[i], NWW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&ofull[i], 1); mbar_init(&ofree[i], C::NEW); }
         mbar_fence_init();
     }
-    if (warp == NWW) {
+    if (warp == NWW + C::NEW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)C::TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -79,7 +88,7 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
     const uint32_t tmem = tmem_slot;
     const int ntile = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-    if (warp == NWW) {
+    if (warp == NWW + C::NEW) {
         // ================= tensor-core warp =================
         if (lane == 0 && ntile > 0) {
             // instruction descriptors: A is K-major here (bit 15 clear), unlike the MN-major operands of the other kernels
@@ -99,23 +108,28 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
                     const int sl = d % C::NS;
                     mbar_wait(&dfull[sl], (d / C::NS) & 1);
                     tc_fence_after();
+                    DTRACE(ti, 8 + cb);
                     const uint64_t db = de0 + (uint64_t)(((uint32_t)sl * C::SLOT * 4) >> 4);
-                    const uint32_t acc = tmem + ob * 192 + cb * 64;
+                    // two independent accumulation chains, interleaved so consecutive MMAs never wait for each other's accumulator:
+                    //   main  (one per step, 9 MMAs): E_hi . [W9hi | W9lo]  -> columns cb * 64 + [0, 64)
+                    //   corr  (one per tile, 27 MMAs): E_lo . W9hi          -> columns 192 + [0, 32)
+                    // (the tensor core accumulates with truncation: the main term gets the short chain, the small correction the long one)
+                    const uint32_t acc = tmem + ob * 224 + cb * 64, corr = tmem + ob * 224 + 192;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int ky = t / 3, kx = t % 3;
                         const uint64_t wb = dw0 + (uint64_t)(((cb * 9 + t) * 512 * 4) >> 4);
                         const uint64_t ao = (uint64_t)((((kx & 1) * C::PLANE + ky * C::ROW + (kx >> 1) * 4) * 4) >> 4);
-                        umma_tf32(acc, db + ao, wb, IDESC_A, t ? 1u : 0u);                                   // E_hi . [W9hi | W9lo]
-                        umma_tf32(acc + 32, db + ao + (uint64_t)((C::HL * 4) >> 4), wb, IDESC_B, 1u);         // E_lo . W9hi -> correction columns
+                        umma_tf32(acc, db + ao, wb, IDESC_A, t ? 1u : 0u);
+                        umma_tf32(corr, db + ao + (uint64_t)((C::HL * 4) >> 4), wb, IDESC_B, (cb | t) ? 1u : 0u);
                     }
                     umma_commit(&dfree[sl]);
+                    DTRACE(ti, 11 + cb);
                 }
                 umma_commit(&ofull[ob]);
             }
         }
     } else {
-        // ================= worker warps =================
         const int tpi = tiles_x * tiles_y;
         const uint32_t inv_tx = (65536u + (uint32_t)tiles_x - 1u) / (uint32_t)tiles_x;
         auto origin = [&](int ti, int& b, int& oy0, int& ox0) {
@@ -125,63 +139,27 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
             const int ty = (int)(((uint32_t)t * inv_tx) >> 16);
             oy0 = ty * C::TH; ox0 = (t - ty * tiles_x) * C::TW;
         };
-        const size_t plane = (size_t)Hin * Win;
-        // x tile [4][RH][2 XWP] of image b at input rows 2 oy0 - 1 .., columns 2 ox0 - 2 .. -> dst, zero outside the image (8-byte cp.async)
-        auto stage_x = [&](int b, int oy0, int ox0, float* dst) {
-            const float* src = x + (size_t)b * 4 * plane;
-            const bool even = (Win & 1) == 0;                        // column pairs never straddle the image edge
-            for (int idx = tid; idx < 4 * C::RH * C::XWP; idx += NTW) {
-                const int k = idx / (C::RH * C::XWP), rem = idx - k * (C::RH * C::XWP);
-                const int r = rem / C::XWP, jp = rem - r * C::XWP;
-                const int gy = 2 * oy0 - 1 + r, gx = 2 * ox0 - 2 + 2 * jp;
-                const bool rowok = (unsigned)gy < (unsigned)Hin;
-                float* dd = dst + (k * C::RH + r) * C::XW + 2 * jp;
-                const float* sp = src + (size_t)k * plane + (size_t)(rowok ? gy : 0) * Win;
-                if (even) {
-                    const bool ok = rowok && (unsigned)gx < (unsigned)Win;
-                    cp_async8(dd, ok ? sp + gx : src, ok ? 8 : 0);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const bool ok = rowok && (unsigned)(gx + e) < (unsigned)Win;
-                        cp_async4(dd + e, ok ? sp + gx + e : src, ok ? 4 : 0);
-                    }
-                }
-            }
-            cp_async_commit();
-        };
-        int tb = 0, oy0 = 0, ox0 = 0, nb = 0, noy0 = 0, nox0 = 0;
-        if (ntile > 0) {
-            origin(0, nb, noy0, nox0);
-            stage_x(nb, noy0, nox0, Xs0);
-        }
-        mbar_wait(&wres, 0);                                         // conv1_8 / bias / conv2_1 weights live behind the B operands
-        // this thread's producer items (fixed for the whole kernel): item = cg * NPIX_IN + input pixel (r, j) -> E entry (cg, parity j & 1, r, j >> 1)
-        int it_x[C::IPT], it_e[C::IPT], it_rj[C::IPT];
-#pragma unroll
-        for (int i = 0; i < C::IPT; ++i) {
-            const int item = min(tid + i * NTW, C::NITEM - 1);
-            const int cg = item / C::NPIX_IN, pi = item - cg * C::NPIX_IN;
-            const int r = pi / C::RW, j = pi - r * C::RW;
-            it_rj[i] = r | (j << 8) | (cg << 16);
-            it_x[i] = r * C::XW + j + 1;                             // staged column index: the tile's column j sits at j + 1
-            it_e[i] = (cg * 2 + (j & 1)) * C::PLANE + r * C::ROW + (j >> 1) * 4;
-        }
-        // epilogue of tile te (thread = pixel; the three warps that share a TMEM lane quarter split the 8 output channels): the three
-        // step accumulators -> + b9, ReLU -> conv2_1 (24 -> 8) in registers -> HBM. Runs one step late (after the first step of the next
-        // tile), so the tensor core never waits for it and the workers never wait for the last MMAs of a tile.
-        const int em = (warp & 3) * 32 + lane, eoy = em >> 3, eox = em & 7, eg = warp >> 2;
-        auto epilogue = [&](int te, int eb, int ey0, int ex0) {
-            const int ob = te & 1;
-            if (eg < 3) {
-                mbar_wait(&ofull[ob], (te >> 1) & 1);
+        if (warp >= NWW) {
+            // ================= epilogue warps (thread = pixel): the three step accumulators (main + hi.lo columns) + the tile's lo.hi
+            // correction + b9, ReLU, conv2_1 (24 -> 8) as FMAs in registers -> HBM. Runs off the producers' path: one tile behind. ====
+            mbar_wait(&wres, 0);
+            const int q = warp - NWW, em = q * 32 + lane, eoy = em >> 3, eox = em & 7;
+            for (int ti = 0; ti < ntile; ++ti) {
+                int eb, ey0, ex0;
+                origin(ti, eb, ey0, ex0);
+                const int ob = ti & 1;
+                mbar_wait(&ofull[ob], (ti >> 1) & 1);
                 tc_fence_after();
-            }
-            float v[24];
-            if (eg < 3) {
-                const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ob * 192;
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + ob * 224;
+                float v[24];
+                {
+                    float c0[16], c1[8];
+                    tmem_ld16(ta + 192, c0); tmem_ld8(ta + 208, c1);                 // the tile's lo . hi correction accumulator
 #pragma unroll
-                for (int n = 0; n < 24; ++n) v[n] = Wr[C::OFF_B9 + n];
+                    for (int n = 0; n < 16; ++n) v[n] = c0[n] + Wr[C::OFF_B9 + n];
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) v[16 + n] = c1[n] + Wr[C::OFF_B9 + 16 + n];
+                }
 #pragma unroll
                 for (int cb = 0; cb < 3; ++cb) {
                     float a0[16], a1[8], l0[16], l1[8];
@@ -192,84 +170,138 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
                     for (int n = 0; n < 8; ++n) v[16 + n] += a1[n] + l1[n];
                 }
                 tc_fence_before();
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ofree[ob]);
-            if (eg >= 3) return;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ofree[ob]);
+                float ps[8];
 #pragma unroll
-            for (int n = 0; n < 24; ++n) v[n] = fmaxf(v[n], 0.f);
-            const int gy = ey0 + eoy, gx = ex0 + eox;
-            if (gy < Hout && gx < Wout) {
+                for (int j = 0; j < 8; ++j) ps[j] = Wr[C::OFF_B21 + j];
 #pragma unroll
-                for (int jj = 0; jj < 3; ++jj) {
-                    const int j = eg * 3 + jj;                       // channels {0,1,2}, {3,4,5}, {6,7}
-                    if (j < 8) {
-                        float r = Wr[C::OFF_B21 + j];
+                for (int n = 0; n < 24; ++n) {
+                    const float vn = fmaxf(v[n], 0.f);
+                    const float4 wa = ld4(Wr + C::OFF_W21 + n * 8), wb = ld4(Wr + C::OFF_W21 + n * 8 + 4);      // [n][j]
+                    ps[0] = fmaf(wa.x, vn, ps[0]); ps[1] = fmaf(wa.y, vn, ps[1]); ps[2] = fmaf(wa.z, vn, ps[2]); ps[3] = fmaf(wa.w, vn, ps[3]);
+                    ps[4] = fmaf(wb.x, vn, ps[4]); ps[5] = fmaf(wb.y, vn, ps[5]); ps[6] = fmaf(wb.z, vn, ps[6]); ps[7] = fmaf(wb.w, vn, ps[7]);
+                }
+                const int gy = ey0 + eoy, gx = ex0 + eox;
+                if (gy < Hout && gx < Wout) {
 #pragma unroll
-                        for (int n4 = 0; n4 < 6; ++n4) {
-                            const float4 w = ld4(Wr + C::OFF_W21 + j * 24 + 4 * n4);
-                            r = fmaf(w.x, v[4 * n4], r); r = fmaf(w.y, v[4 * n4 + 1], r);
-                            r = fmaf(w.z, v[4 * n4 + 2], r); r = fmaf(w.w, v[4 * n4 + 3], r);
-                        }
-                        y[(((size_t)eb * 8 + j) * Hout + gy) * Wout + gx] = r;
-                    }
+                    for (int j = 0; j < 8; ++j) y[(((size_t)eb * 8 + j) * Hout + gy) * Wout + gx] = ps[j];
                 }
             }
-        };
-        int d = 0;
-        for (int ti = 0; ti < ntile; ++ti) {
-            const int pb = tb, poy0 = oy0, pox0 = ox0;               // previous tile (its epilogue is still pending)
-            tb = nb; oy0 = noy0; ox0 = nox0;
-            const bool have_next = ti + 1 < ntile;
-            if (have_next) origin(ti + 1, nb, noy0, nox0);
-            const float* Xs = Xs0 + (ti & 1) * C::XS1;
-            cp_async_wait_all();
-            named_bar_sync<1, NTW>();                                // this tile's x has landed for everyone; the other buffer is free
-            if (have_next) stage_x(nb, noy0, nox0, Xs0 + ((ti + 1) & 1) * C::XS1);
-            // this thread's input pixels: the 4 input channels and whether the pixel lies inside the image
-            float xv[C::IPT][4];
-            bool in[C::IPT];
+        } else {
+            // ================= producer warps =================
+            const size_t plane = (size_t)Hin * Win;
+            // x tile [4][RH][2 XWP] of image b at input rows 2 oy0 - 1 .., columns 2 ox0 - 2 .. -> dst, zero outside the image (8-byte
+            // cp.async); the copies of a thread are the same every tile: (source offset, destination, row, column pair) are precomputed
+            int sg_src[C::SPT], sg_dst[C::SPT], sg_rj[C::SPT];
+#pragma unroll
+            for (int i = 0; i < C::SPT; ++i) {
+                const int idx = min(tid + i * NTW, C::NSTG - 1);
+                const int k = idx / (C::RH * C::XWP), rem = idx - k * (C::RH * C::XWP);
+                const int r = rem / C::XWP, jp = rem - r * C::XWP;
+                sg_src[i] = (int)(k * plane) + r * Win + 2 * jp;
+                sg_dst[i] = (k * C::RH + r) * C::XW + 2 * jp;
+                sg_rj[i] = r | (jp << 8);
+            }
+            const bool even = (Win & 1) == 0;                        // column pairs never straddle the image edge
+            auto stage_x = [&](int b, int oy0, int ox0, float* dst) {
+                const float* src = x + (size_t)b * 4 * plane;
+                const int o0 = (2 * oy0 - 1) * Win + 2 * ox0 - 2;
+#pragma unroll
+                for (int i = 0; i < C::SPT; ++i) {
+                    if (tid + i * NTW < C::NSTG) {
+                        const int gy = 2 * oy0 - 1 + (sg_rj[i] & 255), gx = 2 * ox0 - 2 + 2 * (sg_rj[i] >> 8);
+                        const bool rowok = (unsigned)gy < (unsigned)Hin;
+                        if (even) {
+                            const bool ok = rowok && (unsigned)gx < (unsigned)Win;
+                            cp_async8(dst + sg_dst[i], ok ? src + o0 + sg_src[i] : src, ok ? 8 : 0);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const bool ok = rowok && (unsigned)(gx + e) < (unsigned)Win;
+                                cp_async4(dst + sg_dst[i] + e, ok ? src + o0 + sg_src[i] + e : src, ok ? 4 : 0);
+                            }
+                        }
+                    }
+                }
+                cp_async_commit();
+            };
+            int oy0 = 0, ox0 = 0, nb = 0, noy0 = 0, nox0 = 0;
+            if (ntile > 0) {
+                origin(0, nb, noy0, nox0);
+                stage_x(nb, noy0, nox0, Xs0);
+            }
+            mbar_wait(&wres, 0);                                     // the conv1_8 weights live behind the B operands
+            // this thread's producer items (fixed for the whole kernel): channel group cg = tid / NTH, input pixels pi = (tid % NTH) + i * NTH
+            // -> E entry (cg, parity j & 1, r, j >> 1)
+            const int cg = tid / C::NTH, tl = tid - cg * C::NTH;
+            int it_x[C::IPT], it_e[C::IPT], it_rj[C::IPT];
 #pragma unroll
             for (int i = 0; i < C::IPT; ++i) {
-                in[i] = (unsigned)(2 * oy0 - 1 + (it_rj[i] & 255)) < (unsigned)Hin && (unsigned)(2 * ox0 - 1 + ((it_rj[i] >> 8) & 255)) < (unsigned)Win;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) xv[i][k] = Xs[k * C::RH * C::XW + it_x[i]];
+                const int pi = min(tl + i * C::NTH, C::NPIX_IN - 1);
+                const int r = pi / C::RW, j = pi - r * C::RW;
+                it_rj[i] = r | (j << 8);
+                it_x[i] = r * C::XW + j + 1;                         // staged column index: the tile's column j sits at j + 1
+                it_e[i] = (cg * 2 + (j & 1)) * C::PLANE + r * C::ROW + (j >> 1) * 4;
             }
-#pragma unroll 1
-            for (int cb = 0; cb < 3; ++cb, ++d) {
-                const int sl = d % C::NS;
-                if (d >= C::NS) mbar_wait(&dfree[sl], ((d / C::NS) - 1) & 1);
-                float* Eh = Ebuf + sl * C::SLOT;
+            int d = 0;
+            for (int ti = 0; ti < ntile; ++ti) {
+                oy0 = noy0; ox0 = nox0;
+                const bool have_next = ti + 1 < ntile;
+                if (have_next) origin(ti + 1, nb, noy0, nox0);
+                const float* Xs = Xs0 + (ti & 1) * C::XS1;
+                if (tid == 0) DTRACE(ti, 0);
+                cp_async_wait_all();
+                named_bar_sync<1, NTW>();                            // this tile's x has landed for everyone; the other buffer is free
+                if (tid == 0) DTRACE(ti, 1);
+                if (have_next) stage_x(nb, noy0, nox0, Xs0 + ((ti + 1) & 1) * C::XS1);
+                // this thread's input pixels: the 4 input channels and whether the pixel lies inside the image
+                float xv[C::IPT][4];
+                bool in[C::IPT];
 #pragma unroll
                 for (int i = 0; i < C::IPT; ++i) {
-                    if (tid + i * NTW < C::NITEM) {
-                        const int c0 = cb * 8 + (it_rj[i] >> 16) * 4;  // first of this item's 4 channels
-                        float hi[4], lo[4];
+                    in[i] = (unsigned)(2 * oy0 - 1 + (it_rj[i] & 255)) < (unsigned)Hin && (unsigned)(2 * ox0 - 1 + (it_rj[i] >> 8)) < (unsigned)Win;
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            const float4 w = ld4(Wr + C::OFF_W8 + (c0 + cc) * 4);
-                            float e = fmaf(w.x, xv[i][0], Wr[C::OFF_B8 + c0 + cc]);
-                            e = fmaf(w.y, xv[i][1], e);
-                            e = fmaf(w.z, xv[i][2], e);
-                            e = fmaf(w.w, xv[i][3], e);
-                            e = in[i] ? fmaxf(e, 0.f) : 0.f;          // conv1_9 zero-pads ITS input, the activation
-                            hi[cc] = tf32_hi(e);
-                            lo[cc] = e - hi[cc];
-                        }
-                        st4(Eh + it_e[i], make_float4(hi[0], hi[1], hi[2], hi[3]));
-                        st4(Eh + C::HL + it_e[i], make_float4(lo[0], lo[1], lo[2], lo[3]));
-                    }
+                    for (int k = 0; k < 4; ++k) xv[i][k] = Xs[k * C::RH * C::XW + it_x[i]];
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&dfull[sl]);
-                if (cb == 0 && ti > 0) epilogue(ti - 1, pb, poy0, pox0);
+#pragma unroll 1
+                for (int cb = 0; cb < 3; ++cb, ++d) {
+                    const int sl = d % C::NS;
+                    float4 w8r[4];                                   // conv1_8 weights / bias of this thread's 4 channels in this step
+                    float b8r[4];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) { w8r[cc] = ld4(Wr + C::OFF_W8 + (cb * 8 + cg * 4 + cc) * 4); b8r[cc] = Wr[C::OFF_B8 + cb * 8 + cg * 4 + cc]; }
+                    if (d >= C::NS) mbar_wait(&dfree[sl], ((d / C::NS) - 1) & 1);
+                    if (tid == 0 && cb == 0) DTRACE(ti, 6);
+                    float* Eh = Ebuf + sl * C::SLOT;
+#pragma unroll
+                    for (int i = 0; i < C::IPT; ++i) {
+                        if (tl + i * C::NTH < C::NPIX_IN) {
+                            float hi[4], lo[4];
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                float e = fmaf(w8r[cc].x, xv[i][0], b8r[cc]);
+                                e = fmaf(w8r[cc].y, xv[i][1], e);
+                                e = fmaf(w8r[cc].z, xv[i][2], e);
+                                e = fmaf(w8r[cc].w, xv[i][3], e);
+                                e = in[i] ? fmaxf(e, 0.f) : 0.f;      // conv1_9 zero-pads ITS input, the activation
+                                hi[cc] = tf32_hi(e);
+                                lo[cc] = e - hi[cc];
+                            }
+                            st4(Eh + it_e[i], make_float4(hi[0], hi[1], hi[2], hi[3]));
+                            st4(Eh + C::HL + it_e[i], make_float4(lo[0], lo[1], lo[2], lo[3]));
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&dfull[sl]);
+                    if (tid == 0) DTRACE(ti, 2 + cb);
+                }
             }
         }
-        if (ntile > 0) epilogue(ntile - 1, tb, oy0, ox0);
     }
     __syncthreads();
-    if (warp == NWW) {
+    if (warp == NWW + C::NEW) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TCOLS) : "memory");
     }
