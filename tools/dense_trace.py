@@ -25,11 +25,11 @@ lib = _lib.lib()
 lib.yf_debug_trace.argtypes = [C.c_void_p, C.c_int]
 assert lib.yf_debug_trace(buf, 16 * 64) == 0
 t = [[buf[s * 16 + e] for e in range(16)] for s in range(64)]
-print("tile | x-wait  dfree0  step0  step1  step2  epilogue | tile total || mma: dfull0 issue0 dfull1 issue1 dfull2 issue2 (relative to tile start)")
+print("tile | x-wait  dfree0  step0  step1  step2 | tile total || mma: dfull0 issue0 dfull1 issue1 dfull2 issue2 (relative to tile start) || epilogue: ofull, tmem read, rest")
 for s in range(3, 17):
     w = t[s]
     if not w[0] or not t[s + 1][0]:
         break
-    print("%4d | %6d %6d %6d %8d %6d %6d | %7d || %6d %6d %6d %6d %6d %6d" % (
-        s, w[1] - w[0], w[6] - w[1], w[2] - w[6], w[3] - w[2], w[4] - w[3], w[5] - w[4], t[s + 1][0] - w[0],
-        w[8] - w[0], w[11] - w[8], w[9] - w[0], w[12] - w[9], w[10] - w[0], w[13] - w[10]))
+    print("%4d | %6d %6d %6d %8d %6d | %7d || %6d %6d %6d %6d %6d %6d || %6d %6d %6d" % (
+        s, w[1] - w[0], w[6] - w[1], w[2] - w[6], w[3] - w[2], w[4] - w[3], t[s + 1][0] - w[0],
+        w[8] - w[0], w[11] - w[8], w[9] - w[0], w[12] - w[9], w[10] - w[0], w[13] - w[10], w[5] - w[0], w[7] - w[5], w[14] - w[7]))

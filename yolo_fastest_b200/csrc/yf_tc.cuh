@@ -51,6 +51,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// true in exactly one lane of a converged warp; unlike (lane == 0) the compiler knows the branch holds a single thread, so it issues
+// the uniform-datapath tcgen05 instructions directly instead of wrapping each in an ELECT / BRA.U.ANY loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -257,7 +264,7 @@ irbtc_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __
 
     if (warp == NWW) {
         // ================= tensor-core warp: one thread issues every MMA and every weight copy =================
-        if (lane == 0 && S > 0) {
+        if (S > 0 && elect_one()) {
             constexpr uint32_t IDESC1 = umma_idesc_tf32(C::N1), IDESC3A = umma_idesc_tf32(2 * C::COUTP), IDESC3B = umma_idesc_tf32(C::COUTP);
             const uint32_t xh = smem_u32(XAhi), xl = smem_u32(XAlo), dh = smem_u32(DAhi), dl = smem_u32(DAlo), ws = smem_u32(Ws);
             auto issue_w = [&](int s) {

@@ -82,7 +82,7 @@ irbtc2_kernel(const float* __restrict__ x, float* __restrict__ y, const float* _
 
     if (warp == NWW) {
         // ================= tensor-core warp =================
-        if (lane == 0 && ntile > 0) {
+        if (ntile > 0 && elect_one()) {
             constexpr uint32_t IDESC_A = umma_idesc_tf32(C::NA), IDESC_B = umma_idesc_tf32(C::COUTP);
             const int S = ntile * C::STEPS;
             const uint64_t dd0 = umma_desc(smem_u32(Dbuf), 1024, 512, 1);

@@ -133,7 +133,7 @@ dwpw_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float* 
 
     if (warp == NWW) {
         // ================= tensor-core warp =================
-        if (lane == 0 && S > 0) {
+        if (S > 0 && elect_one()) {
             constexpr uint32_t IDESC = umma_idesc_tf32(C::NP);
             const uint32_t ws = smem_u32(Ws);
             auto issue_w = [&](int q) {

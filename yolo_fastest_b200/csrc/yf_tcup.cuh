@@ -78,7 +78,7 @@ upcat_tc_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __r
 
     if (warp == NWW) {
         // ================= tensor-core warp =================
-        if (lane == 0 && ntile > 0) {
+        if (ntile > 0 && elect_one()) {
             constexpr uint32_t IDESC_A = umma_idesc_tf32(C::NHALF), IDESC_B = umma_idesc_tf32(C::N);
             const int S = ntile * C::STEPS;
             const uint64_t dd0 = umma_desc(smem_u32(Dbuf), 1024, 512, 1);
