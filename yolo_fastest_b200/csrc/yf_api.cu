@@ -233,11 +233,14 @@ using CfgRes3b = YF_CFGRES3B;
 #define YF_TC3_RH 8
 #define YF_TC3_NWW 10
 #endif
+#ifndef YF_TC3_OCC
+#define YF_TC3_OCC 1
+#endif
 #ifndef YF_TC3_E1ALL
 #define YF_TC3_E1ALL false
 #endif
 #ifndef YF_CFGRES3B_TC
-#define YF_CFGRES3B_TC IrbTcCfg<16, 96, 16, YF_TC3_TH, YF_TC3_TW, YF_TC3_MC, YF_TC3_RH, YF_TC3_NWW, true, YF_TC3_E1ALL>
+#define YF_CFGRES3B_TC IrbTcCfg<16, 96, 16, YF_TC3_TH, YF_TC3_TW, YF_TC3_MC, YF_TC3_RH, YF_TC3_NWW, true, YF_TC3_E1ALL, YF_TC3_OCC>
 #endif
 using CfgRes3bTc = YF_CFGRES3B_TC;
 #ifndef YF_CFGRES4_TC

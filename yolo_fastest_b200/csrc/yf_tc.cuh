@@ -115,8 +115,9 @@ constexpr int e_stride(int ipix, int nstrip) {
     return v;
 }
 
-template <int CIN_, int CMID_, int COUT_, int TH_, int TW_, int MC_, int RH_, int NWW_, bool RES_, bool E1ALL_ = true>
+template <int CIN_, int CMID_, int COUT_, int TH_, int TW_, int MC_, int RH_, int NWW_, bool RES_, bool E1ALL_ = true, int OCC_ = 1>
 struct IrbTcCfg {
+    static constexpr int OCC = OCC_;              // CTAs per SM the kernel is compiled for (register cap, TMEM columns)
     static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_, MC = MC_, RH = RH_, NWW = NWW_;
     static constexpr int NTW = NWW * 32;          // worker threads
     static constexpr int NT = NTW + 32;           // + the tensor-core warp
@@ -153,7 +154,7 @@ struct IrbTcCfg {
     static constexpr int NIT = cdiv(NITEM_X, NTW);                // ... per worker thread
     static_assert(CIN % 8 == 0 && MC % 16 == 0 && NWW >= 4, "tcgen05 tiling constraints");
     static_assert(N1 % 16 == 0 && N1 <= 256, "expand MMA N");
-    static_assert(TCOLS <= 512, "TMEM columns");
+    static_assert(TCOLS * OCC <= 512, "TMEM columns");
     static_assert(!RES || CIN == COUT, "residual needs same shape");
     static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
     static_assert(W1RES % 32 == 0, "resident weights: 128-byte granularity");
@@ -225,7 +226,7 @@ __device__ __forceinline__ void dw_stage_split(int tid, const float* __restrict_
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, 1)
+__global__ void __launch_bounds__(C::NT, C::OCC)
 irbtc_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts, int H, int W,
              int tiles_x, int tiles_y, int total_tiles) {
     using G = typename C::G;

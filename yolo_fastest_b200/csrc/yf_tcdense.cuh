@@ -134,12 +134,8 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
                         const int ky = t / 3, kx = t % 3;
                         const uint64_t wb = dw0 + (uint64_t)(((cb * 9 + t) * 512 * 4) >> 4);
                         const uint64_t ao = (uint64_t)((((kx & 1) * C::PLANE + ky * C::ROW + (kx >> 1) * 4) * 4) >> 4);
-#if !defined(YF_DENSE_EXP) || YF_DENSE_EXP != 1
                         umma_tf32(acc, db + ao, wb, IDESC_A, t ? 1u : 0u);
-#endif
-#if !defined(YF_DENSE_EXP) || YF_DENSE_EXP != 2
                         umma_tf32(corr, db + ao + (uint64_t)((C::HL * 4) >> 4), wb, IDESC_B, (cb | t) ? 1u : 0u);
-#endif
                     }
                     umma_commit(&dfree[sl]);
                     DTRACE(ti, 11 + cb);
