@@ -180,6 +180,21 @@ int yf_detect_wait(yf_ctx* ctx, int slot);
 int yf_detect_submit_u8_dev(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
                             yf_det* out_dev, int32_t* counts_dev, int32_t* status_dev);
 
+/* ---- pre-processing on the device ------------------------------------------ */
+
+/* Replaces the image half of Detect_YOLO.__pre_process (detect.py:107-122): cv2.cvtColor(BGR2GRAY) followed by
+ * cv2.resize(img, (W, H)) (INTER_LINEAR) for a batch of frames as cv2.imread returns them.
+ * bgr dev [B, Ho, Wo, 3] uint8 (interleaved B, G, R) -> gray dev [B, H, W] uint8, H and W those of yf_create.
+ * Integer arithmetic identical to OpenCV 4.x for 8-bit images, so the bytes equal the host path's; with
+ * Ho == H and Wo == W the resize is the identity, as in the reference, which then skips it. The normalisation
+ * (x - 128) / 255 (detect.py:124) stays fused into the first convolution of the u8 entry points. */
+int yf_preprocess_bgr(yf_ctx* ctx, const uint8_t* bgr, int B, int Ho, int Wo, uint8_t* gray, void* stream);
+
+/* yf_detect_host_u8 with that pre-processing in front: bgr_host [B, Ho, Wo, 3] uint8 host frames -> detections in
+ * NETWORK-input coordinates (Detect_YOLO.__adjust_coord, detect.py:131-139, stays with the caller). */
+int yf_detect_host_bgr(yf_ctx* ctx, const uint8_t* bgr_host, int B, int Ho, int Wo, const yf_post_params* p,
+                       yf_det* out_host, int32_t* counts_host, int32_t* status_host, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 
 /* Kernels launched by this ctx since creation (the bench's gpu_launches evidence). */

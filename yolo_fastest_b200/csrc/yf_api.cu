@@ -20,6 +20,7 @@
 #include "yf_tcup.cuh"
 #include "yf_tcirb2.cuh"
 #include "yf_tcdense.cuh"
+#include "yf_prep.cuh"
 
 using namespace yf;
 
@@ -163,6 +164,11 @@ struct yf_ctx {
     bool sl_used[2] = {false, false};
     // CUDA graphs of forward + head kernel on the library's own fixed buffers (small batches: launch latency dominates)
     std::map<std::string, std::pair<cudaGraphExec_t, int>> graphs;    // key -> (executable graph, kernel launches inside)
+    // GPU pre-processing (yf_preprocess_bgr / yf_detect_host_bgr): coefficient tables of the last source size, BGR staging
+    PrepTap* prep_tab = nullptr;                        // [W column taps | H row taps]
+    int prep_Ho = 0, prep_Wo = 0;
+    unsigned char* d_bgr = nullptr;
+    size_t bgr_cap = 0;
     unsigned char* n_alive = nullptr;                   // yf_nms_sorted_* scratch
     int n_alive_cap = 0;
     int64_t launches = 0;
@@ -1067,7 +1073,7 @@ extern "C" void yf_destroy(yf_ctx* ctx) {
     cudaFree(ctx->d_w); cudaFree(ctx->d_skip); cudaFree(ctx->d_hl); cudaFree(ctx->d_hs); cudaFree(ctx->d_x); cudaFree(ctx->d_u8);
     cudaFree(ctx->d_out); cudaFree(ctx->d_counts); cudaFree(ctx->d_status);
     cudaFree(ctx->p_rec); cudaFree(ctx->p_conf); cudaFree(ctx->p_cls); cudaFree(ctx->p_sbox); cudaFree(ctx->p_order);
-    cudaFree(ctx->p_alive); cudaFree(ctx->n_alive);
+    cudaFree(ctx->p_alive); cudaFree(ctx->n_alive); cudaFree(ctx->prep_tab); cudaFree(ctx->d_bgr);
     for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);
     if (ctx->s_cap) cudaStreamDestroy(ctx->s_cap);
     if (ctx->s_copy) {
@@ -1432,6 +1438,74 @@ extern "C" int yf_detect_host_u8(yf_ctx* ctx, const uint8_t* u8_host, int B, con
                                  int32_t* counts_host, int32_t* status_host, void* stream) {
     CTX_CHECK(ctx);
     return detect_host_impl(ctx, u8_host, true, B, p, out_host, counts_host, status_host, (cudaStream_t)stream);
+}
+
+// ---- GPU pre-processing: BGR frames -> gray -> bilinear resize to the network input (detect.py:107-122) ------------------------
+static int prep_enqueue(yf_ctx* ctx, const uint8_t* bgr_dev, int B, int Ho, int Wo, uint8_t* gray_dev, cudaStream_t st) {
+    if (ctx->in_ch != 1) { set_err(&ctx->err, "pre-processing serves the single-channel models"); return YF_ERR_STATE; }
+    if (Ho < 1 || Wo < 1 || Ho > 16384 || Wo > 16384) { set_err(&ctx->err, "source size %dx%d not supported", Ho, Wo); return YF_ERR_ARG; }
+    if (Ho != ctx->prep_Ho || Wo != ctx->prep_Wo) {
+        std::vector<PrepTap> tab((size_t)ctx->W + ctx->H);
+        prep_taps(ctx->W, Wo, false, tab.data());
+        prep_taps(ctx->H, Ho, true, tab.data() + ctx->W);
+        if (!ctx->prep_tab) CU(cudaMalloc(&ctx->prep_tab, sizeof(PrepTap) * tab.size()));
+        CU(cudaStreamSynchronize(st));                  // a kernel enqueued earlier may still read the old tables
+        CU(cudaMemcpy(ctx->prep_tab, tab.data(), sizeof(PrepTap) * tab.size(), cudaMemcpyHostToDevice));
+        ctx->prep_Ho = Ho; ctx->prep_Wo = Wo;
+    }
+    const int nsm = ctx->groups.empty() ? 148 : ctx->groups[0].a.nsm;
+    const int W4 = ctx->W / 4, Wo4 = Wo / 4;
+    const int nt = Wo4 > 0 && Wo4 <= 512 ? (512 / Wo4) * Wo4 : Wo4;       // staging threads: a whole number of frame rows
+    const size_t smem = (size_t)2 * PREP_R * Wo;
+    if (Wo % 4 == 0 && nt >= 32 && nt <= 1024 && W4 <= nt && smem <= 48 * 1024 && ((uintptr_t)bgr_dev & 3) == 0) {
+        const long long groups = (long long)B * ((ctx->H + PREP_R - 1) / PREP_R);
+        const int grid = (int)std::min<long long>(groups, (long long)nsm * (2048 / nt));
+        prep_bgr_rows_kernel<<<grid, nt, smem, st>>>(bgr_dev, gray_dev, ctx->prep_tab, ctx->prep_tab + ctx->W, B, Ho, Wo, ctx->H, ctx->W);
+    } else {                                            // any width / alignment: one thread per 4 output pixels, byte loads
+        const long long total = (long long)B * ctx->H * W4;
+        const int grid = (int)std::min<long long>((total + 255) / 256, (long long)nsm * 16);
+        prep_bgr_kernel<<<grid, 256, 0, st>>>(bgr_dev, gray_dev, ctx->prep_tab, ctx->prep_tab + ctx->W, B, Ho, Wo, ctx->H, ctx->W);
+    }
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return YF_OK;
+}
+
+extern "C" int yf_preprocess_bgr(yf_ctx* ctx, const uint8_t* bgr_dev, int B, int Ho, int Wo, uint8_t* gray_dev, void* stream) {
+    CTX_CHECK(ctx);
+    if (!bgr_dev || !gray_dev || B < 1) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
+    CU(cudaSetDevice(ctx->device));
+    return prep_enqueue(ctx, bgr_dev, B, Ho, Wo, gray_dev, (cudaStream_t)stream);
+}
+
+extern "C" int yf_detect_host_bgr(yf_ctx* ctx, const uint8_t* bgr_host, int B, int Ho, int Wo, const yf_post_params* p,
+                                  yf_det* out_host, int32_t* counts_host, int32_t* status_host, void* stream) {
+    CTX_CHECK(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!bgr_host || !p || !out_host || !counts_host) { set_err(&ctx->err, "null argument"); return YF_ERR_ARG; }
+    if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
+    if (p->max_det < 1) { set_err(&ctx->err, "max_det must be >= 1"); return YF_ERR_ARG; }
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_out(ctx, p->max_det);
+    if (rc) return rc;
+    const size_t nbytes = (size_t)B * Ho * Wo * 3;
+    if (nbytes > ctx->bgr_cap) {
+        CU(cudaStreamSynchronize(st));
+        if (ctx->d_bgr) CU(cudaFree(ctx->d_bgr));
+        ctx->d_bgr = nullptr; ctx->bgr_cap = 0;
+        CU(cudaMalloc(&ctx->d_bgr, nbytes));
+        ctx->bgr_cap = nbytes;
+    }
+    CU(cudaMemcpyAsync(ctx->d_bgr, bgr_host, nbytes, cudaMemcpyHostToDevice, st));
+    rc = prep_enqueue(ctx, ctx->d_bgr, B, Ho, Wo, ctx->d_u8, st);
+    if (rc) return rc;
+    rc = detect_fixed(ctx, ctx->d_u8, true, B, p, ctx->d_out, ctx->d_counts, ctx->d_status, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_host, ctx->d_out, sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(counts_host, ctx->d_counts, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    if (status_host) CU(cudaMemcpyAsync(status_host, ctx->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return YF_OK;
 }
 
 // ---- asynchronous, double-buffered host path --------------------------------------------------------------

@@ -194,6 +194,62 @@ class Detect_YOLO:
             r[1] = round(r[1] * scale_h)
             r[3] = round(r[3] * scale_h)
 
+    # ---- pre-processing on the device (detect.py:107-122) ------------------------------------
+    def pre_process_batch(self, bgr):
+        """BGR uint8 frames [B, Ho, Wo, 3] as cv2.imread returns them (host numpy / torch, or a cuda uint8 tensor) ->
+        cuda uint8 [B, H, W]: cv2.cvtColor(BGR2GRAY) + cv2.resize(INTER_LINEAR) computed on the device, byte-identical
+        to the host path (yf_preprocess_bgr). The normalisation is applied by the first convolution of the u8 paths."""
+        t = bgr if isinstance(bgr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bgr, dtype=np.uint8))
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != 3:
+            raise _lib.YfError("pre_process_batch takes uint8 frames [B, Ho, Wo, 3]")
+        t = t.to(self.device).contiguous()
+        B, Ho, Wo, _ = t.shape
+        H, W = self.input_shape[0:2]
+        ctx = self.model.context(self.device, H, W, B)
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().yf_preprocess_bgr(ctx.handle, t.data_ptr(), B, Ho, Wo, out.data_ptr(), C.c_void_p(stream)), ctx.handle)
+        return out
+
+    def detect_bgr_batch(self, bgr, max_det=64, raw=False, adjust=True):
+        """Frames as cv2.imread returns them, uint8 [B, Ho, Wo, 3] on the host -> per-image rows: one yf_detect_host_bgr
+        call (H2D of the frames, gray + resize + normalisation + forward + decode + NMS on the device, D2H of the result
+        slab). With adjust=True the boxes are mapped back to the frame like Detect_YOLO.__adjust_coord (detect.py:131-139,
+        applied when the frame and network sizes differ, as batch_detect does)."""
+        t = bgr if isinstance(bgr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bgr, dtype=np.uint8))
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != 3 or t.is_cuda:
+            raise _lib.YfError("detect_bgr_batch takes host uint8 frames [B, Ho, Wo, 3]")
+        t = t.contiguous()
+        B, Ho, Wo, _ = t.shape
+        H, W = self.input_shape[0:2]
+        ctx = self.model.context(self.device, H, W, B)
+        pin_out = torch.empty((B, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+        pin_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
+        pin_st = torch.empty((B,), dtype=torch.int32).pin_memory()
+        p = self.post_process._params(_lib.MODE_DETECT, max_det)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().yf_detect_host_bgr(ctx.handle, t.data_ptr(), B, Ho, Wo, C.byref(p), pin_out.data_ptr(),
+                                                    pin_cnt.data_ptr(), pin_st.data_ptr(), C.c_void_p(stream)), ctx.handle)
+        if (pin_st.numpy() & 1).any():
+            raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
+        counts = pin_cnt.numpy()
+        dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
+        res = [dets[b, :min(int(counts[b]), max_det)].copy() for b in range(B)]
+        if raw:
+            return res
+        rows = [_rows_from_dets(d) for d in res]
+        if adjust and [Ho, Wo] != [H, W]:
+            scale_h, scale_w = Ho / H, Wo / W
+            for rr in rows:
+                for r in rr:
+                    r[0] = round(r[0] * scale_w)
+                    r[2] = round(r[2] * scale_w)
+                    r[1] = round(r[1] * scale_h)
+                    r[3] = round(r[3] * scale_h)
+        return rows
+
     # ---- batched detection through the C ABI with host buffers -----------------------------------------
     def detect_batch(self, u8_batch, max_det=64, raw=False):
         """uint8 gray images [B, H, W] (host numpy array or host torch tensor, network input size) -> per-image rows.
@@ -351,3 +407,34 @@ class Detect_YOLO:
                                  % (filename, infer_time, post_process_time, total_time))
 
             self.logger.info("detect avg_time: %.2fms" % (avg_time / num))
+
+    def batch_detect_batched(self, data_path, result_path, batch_size=32):
+        """batch_detect with the per-file loop turned into batches: the frames of `batch_size` files are
+        decoded on the host (cv2.imread), everything else - gray, resize, normalisation, forward, decode, NMS - is ONE
+        yf_detect_host_bgr call per batch. Same result files and log lines as batch_detect (detect.py:141-192); the two
+        per-image times of the log line are the batch's time divided by its size. Frames of one batch must share a size."""
+        import cv2
+        img_list = os.listdir(data_path)
+        num = len(img_list)
+        avg_time = 0
+        for i0 in range(0, num, batch_size):
+            names = img_list[i0:i0 + batch_size]
+            frames = [cv2.imread(os.path.join(data_path, n)) for n in names]
+            torch.cuda.synchronize(self.device)
+            start_time = time.time()
+            rows = self.detect_bgr_batch(np.stack(frames))
+            total_time = float(time.time() - start_time) * 1000 / len(names)
+            avg_time += total_time * len(names)
+            for filename, ori_img, all_bbox_rects in zip(names, frames, rows):
+                if len(all_bbox_rects) == 0:
+                    cv2.imwrite(os.path.join(result_path, 'result_' + filename), ori_img)
+                    self.logger.info("image_name:%s -> no targets, infer time:%.2fms, post_process time:%.2fms, total time:%.2fms"
+                                     % (filename, total_time, 0.0, total_time))
+                    continue
+                for *xyxy, conf, cls_score, cls_pred in all_bbox_rects:
+                    label = '%s %.2f' % (self.class_names[int(cls_pred)], conf * cls_score)
+                    plot_one_box(xyxy, ori_img, label=label, color=self.colors[int(cls_pred)], line_thickness=3)
+                cv2.imwrite(os.path.join(result_path, 'result_' + filename), ori_img)
+                self.logger.info("image_name:%s -> detect finished, infer time:%.2fms, post_process time:%.2fms, total time:%.2fms"
+                                 % (filename, total_time, 0.0, total_time))
+        self.logger.info("detect avg_time: %.2fms" % (avg_time / max(num, 1)))
