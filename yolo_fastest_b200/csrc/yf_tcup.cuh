@@ -170,33 +170,53 @@ upcat_tc_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __r
         const float* bt = wts + C::OFF_BT;
         const float* bo = wts + C::OFF_B;
 
-        // parent tile [96][4 x 10] of image b -> split operand of GEMM A (item = 8 channels of one parent pixel)
-        auto put_parent = [&](int b, int oy0, int ox0) {
-            constexpr int NITEM = (C::CU / 8) * C::PPIX;
-            for (int item = tid; item < NITEM; item += NTW) {
+        // parent tile [96][4 x 10] of image b -> split operand of GEMM A (item = 8 channels of one parent pixel); the values are
+        // fetched into registers early (unconditional clamped loads) and written once the operand buffer is free
+        constexpr int NITEM_P = (C::CU / 8) * C::PPIX, NIT_P = (NITEM_P + NTW - 1) / NTW;
+        float pr[NIT_P * 8];
+        uint32_t pok = 0;
+        auto fetch_parent = [&](int b, int oy0, int ox0) {
+            pok = 0;
+#pragma unroll
+            for (int i = 0; i < NIT_P; ++i) {
+                const int item = min(tid + i * NTW, NITEM_P - 1);
                 const int kh = item / C::PPIX, pp = item - kh * C::PPIX;
                 const int yy = pp / C::PW, xx = pp - yy * C::PW;
                 const int gy = oy0 / 2 + yy, gx = ox0 / 2 + xx;
                 const bool ok = gy < Hp && gx < Wp;
+                pok |= (ok ? 1u : 0u) << i;
                 const float* src = low + ((size_t)b * C::CU + kh * 8) * pplane + (size_t)(ok ? gy : 0) * Wp + (ok ? gx : 0);
-                const int ob = kh * C::KBP + (pp >> 5) * 256 + (pp & 7), mc = (pp & 31) >> 3;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const float v = ok ? __ldg(src + kk * pplane) : 0.f;
-                    const float hi = tf32_hi(v);
-                    const int o = ob + ((kk >> 2) & 1) * 128 + (kk & 3) * 32 + ((mc ^ (kk & 3)) << 3);
-                    Pbuf[o] = hi;
-                    Pbuf[C::PA1 + o] = v - hi;
+                for (int kk = 0; kk < 8; ++kk) pr[i * 8 + kk] = __ldg(src + kk * pplane);
+            }
+        };
+        auto put_parent = [&]() {
+#pragma unroll
+            for (int i = 0; i < NIT_P; ++i) {
+                const int item = tid + i * NTW;
+                if (item < NITEM_P) {
+                    const int kh = item / C::PPIX, pp = item - kh * C::PPIX;
+                    const int ob = kh * C::KBP + (pp >> 5) * 256 + (pp & 7), mc = (pp & 31) >> 3;
+                    const bool ok = (pok >> i) & 1u;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const float v = ok ? pr[i * 8 + kk] : 0.f;
+                        const float hi = tf32_hi(v);
+                        const int o = ob + ((kk >> 2) & 1) * 128 + (kk & 3) * 32 + ((mc ^ (kk & 3)) << 3);
+                        Pbuf[o] = hi;
+                        Pbuf[C::PA1 + o] = v - hi;
+                    }
                 }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&pfull);
         };
-        // skip chunk: item = (channel, row, 4-pixel group) -> one 128-bit load; two items per thread, fetched one chunk ahead
+        // skip chunk: item = (channel, row, 4-pixel group) -> one 128-bit load; two items per thread, fetched TWO chunks ahead into
+        // alternating register buffers (one chunk step is shorter than the HBM/L2 latency)
         constexpr int SK_ITEMS = C::SK_ITEMS, SK_PER = C::SK_PER;
-        float4 sk[SK_PER];
-        auto fetch_skip = [&](int b, int oy0, int ox0, int c) {
+        float4 skA[SK_PER], skB[SK_PER];
+        auto fetch_skip = [&](int b, int oy0, int ox0, int c, float4 (&sk)[SK_PER]) {
 #pragma unroll
             for (int k = 0; k < SK_PER; ++k) {
                 const int item = min(tid + k * NTW, SK_ITEMS - 1);
@@ -206,7 +226,7 @@ upcat_tc_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __r
                 sk[k] = __ldg(reinterpret_cast<const float4*>(skip + ((size_t)b * C::CS + cg) * plane + (size_t)gy * W + gx));
             }
         };
-        auto put_skip = [&](int c, float* Dh) {
+        auto put_skip = [&](int c, float* Dh, const float4 (&sk)[SK_PER]) {
 #pragma unroll
             for (int k = 0; k < SK_PER; ++k) {
                 const int item = tid + k * NTW;
@@ -251,7 +271,10 @@ upcat_tc_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __r
         int tb = 0, oy0 = 0, ox0 = 0, nb = 0, noy0 = 0, nox0 = 0;
         if (ntile > 0) {
             origin(0, nb, noy0, nox0);
-            put_parent(nb, noy0, nox0);
+            fetch_parent(nb, noy0, nox0);
+            fetch_skip(nb, noy0, nox0, 0, skA);
+            fetch_skip(nb, noy0, nox0, 1, skB);
+            put_parent();
         }
         int d = 0;                                                   // operand-chunk step (global)
         auto chunk_begin = [&]() -> float* {
@@ -269,13 +292,23 @@ upcat_tc_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __r
             tb = nb; oy0 = noy0; ox0 = nox0;
             const bool have_next = ti + 1 < ntile;
             if (have_next) origin(ti + 1, nb, noy0, nox0);
-            fetch_skip(tb, oy0, ox0, 0);
 #pragma unroll 1
-            for (int c = 0; c < C::NSKIP; ++c) {
+            for (int c = 0; c < C::NSKIP; c += 2) {                  // chunks c (buffer A) and c + 1 (buffer B)
                 float* Dh = chunk_begin();
-                put_skip(c, Dh);
-                if (c + 1 < C::NSKIP) fetch_skip(tb, oy0, ox0, c + 1);
+                put_skip(c, Dh, skA);
                 chunk_end();
+                if (c + 2 < C::NSKIP) fetch_skip(tb, oy0, ox0, c + 2, skA);
+                if (c + 1 < C::NSKIP) {
+                    Dh = chunk_begin();
+                    put_skip(c + 1, Dh, skB);
+                    chunk_end();
+                    if (c + 3 < C::NSKIP) fetch_skip(tb, oy0, ox0, c + 3, skB);
+                }
+            }
+            if (have_next) {                                         // the next tile's first loads travel during the up chunks and the epilogue
+                fetch_skip(nb, noy0, nox0, 0, skA);
+                fetch_skip(nb, noy0, nox0, 1, skB);
+                fetch_parent(nb, noy0, nox0);
             }
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
@@ -291,7 +324,7 @@ upcat_tc_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __r
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ufree);
             }
-            if (have_next) put_parent(nb, noy0, nox0);               // GEMM A of the second half is complete: the parent operand is free
+            if (have_next) put_parent();                             // GEMM A of the second half is complete: the parent operand is free
             // ---- epilogue: TMEM O -> + b, ReLU -> HBM (thread = pixel) ----
             mbar_wait(&ofull, ti & 1);
             tc_fence_after();
