@@ -118,3 +118,61 @@ def test_async_double_buffered_serving_loop(gold):
     assert got == want
     with pytest.raises(yf.YfError):
         det.submit_batch(g["u8"][:2], 0)            # not a host tensor
+
+
+def test_full_size_batch_256_properties(gold):
+    """BASELINE.json's headline configuration (640x512, batch 256) through the C ABI, checked by size-independent properties:
+    image independence (the batch equals its four 64-image quarters and a permutation of itself, bit for bit), agreement of
+    the blocking, asynchronous and device-resident entry points, and the oracle on a sample of the images (heads within 1e-4,
+    detections box for box). The 256 inputs are the 20 shipped frames, each rolled by a different offset so every image differs
+    and most of them have detections."""
+    res = "512x640"
+    g = gold.res[res]
+    det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_" + res), yf.config_for(res), None)
+    base = g["u8"]
+    B = 256
+    u8 = np.stack([np.roll(base[i % len(base)], (3 * (i // len(base)), 7 * (i // len(base))), axis=(0, 1)) for i in range(B)])
+    rows = det.detect_batch(u8, max_det=32)
+    assert len(rows) == B and sum(1 for r in rows if r) > B // 2
+    # quarters and a permutation: no image sees its neighbours
+    for q in range(4):
+        assert det.detect_batch(u8[64 * q:64 * q + 64], max_det=32) == rows[64 * q:64 * q + 64]
+    perm = np.random.default_rng(5).permutation(B)
+    assert det.detect_batch(u8[perm], max_det=32) == [rows[i] for i in perm]
+    # asynchronous double-buffered entry point
+    pin = torch.from_numpy(u8).pin_memory()
+    det.submit_batch(pin, 0, max_det=32)
+    assert det.collect(0) == rows
+    # device-resident entry point on the normalised fp32 batch
+    x = ((torch.from_numpy(u8).cuda().float().unsqueeze(1) - 128.0) / 255.0).contiguous()
+    out, counts, status = det.detect_device(x, max_det=32)
+    torch.cuda.synchronize()
+    assert int(status.max()) == 0
+    assert [min(int(c), 32) for c in counts.cpu()] == [len(r) for r in rows]
+    # the oracle on a sample
+    sd = gold.sd("yolo_fastest_" + res)
+    io = yf.config_for(res)["io_params"]
+    hl, hs = det.model(x[[0, 77, 131, 255]])
+    for k, i in enumerate((0, 77, 131, 255)):
+        rl, rs = O.forward(sd, O.preprocess_gray(u8[i]))
+        for got_h, ref_h in ((hl[k].cpu(), rl[0]), (hs[k].cpu(), rs[0])):          # within 1e-4 of the tensor's scale (test_forward_gpu._close)
+            assert float((got_h - ref_h).abs().max()) <= 1e-4 * float(ref_h.abs().max()), i
+        want = O.detect_postprocess((rl, rs), io["anchors"], io["input_shape"], io["conf_thre"], io["nms_thre"], io["num_anchors"], io["num_cls"])
+        _match([list(r) for r in want], rows[i])
+
+
+def test_ncnn_weight_source(gold):
+    """Weights taken from the reference's ncnn deployment files (YoloFastest.load_ncnn) give the shipped checkpoint's results:
+    heads within 1e-4 of the oracle's, the golden detections box for box."""
+    res = "256x320"
+    g = gold.res[res]
+    det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_" + res), yf.config_for(res), None)
+    det.model.load_ncnn(os.path.join(GOLD, "ncnn", "YOLO-Fastest_epoch_28-opt.param"), os.path.join(GOLD, "ncnn", "YOLO-Fastest_epoch_28-opt.bin"))
+    rows = det.detect_batch(g["u8"], max_det=16)
+    for i in range(len(g["u8"])):
+        _match([list(r) for r in g["kept_%02d" % i]], rows[i])
+    x = torch.cat([O.preprocess_gray(u) for u in g["u8"][:3]], 0)
+    rl, rs = O.forward(gold.sd("yolo_fastest_" + res), x)
+    hl, hs = det.model(x.cuda())
+    for got_h, ref_h in ((hl.cpu(), rl), (hs.cpu(), rs)):
+        assert float((got_h - ref_h).abs().max()) <= 1e-4 * float(ref_h.abs().max())

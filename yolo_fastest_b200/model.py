@@ -174,6 +174,50 @@ class YoloFastest(nn.Module):
             raise _lib.YfError("folded blob has %d floats, library expects %d" % (blob.size, expect))
         return blob
 
+    def load_ncnn(self, param_path, bin_path):
+        """Take the weights from the reference's ncnn deployment files (`models/ncnn/<res>/*-opt.param|bin`) instead
+        of a `.pth`. The ncnn network is already BN-folded, so every conv receives the folded kernel and its BatchNorm becomes the
+        identity carrying the folded bias (weight 1, running_mean 0, running_var 1, eps 0, bias b'): `folded_blob` then reproduces
+        the ncnn arrays bit for bit. The layer table is checked against the architecture first."""
+        from . import ncnn_loader
+        layers = ncnn_loader.read_ncnn(param_path, bin_path)
+        slots = []                                   # (conv module, bn module or None, transposed)
+        for name, kind, *_ in ARCH:
+            mod = getattr(self, name)
+            if kind == "cbr":
+                slots.append((mod[0], mod[1], False))
+            elif kind == "res":
+                slots.extend((sub[0], sub[1], False) for sub in (mod.conv1, mod.conv2, mod.conv3))
+            elif kind == "head":
+                slots.append((mod, None, False))
+            else:
+                slots.append((mod[0], mod[1], True))
+        if len(layers) != len(slots):
+            raise _lib.YfError("ncnn file has %d convolutions, YOLO-Fastest has %d" % (len(layers), len(slots)))
+        with torch.no_grad():
+            for (conv, bn, transposed), l in zip(slots, layers):
+                w = torch.from_numpy(l["weight"])
+                cout = conv.weight.shape[1] * conv.groups if transposed else conv.weight.shape[0]
+                if w.numel() != conv.weight.numel() or l["num_output"] != cout or l["kernel"] != conv.kernel_size[0] \
+                        or l["bias"] is None or transposed != l["type"].startswith("Deconv"):
+                    raise _lib.YfError("ncnn layer %s (%s, %d outputs, kernel %d, %d weights) does not match %s"
+                                       % (l["name"], l["type"], l["num_output"], l["kernel"], w.numel(), tuple(conv.weight.shape)))
+                if transposed:                       # ncnn stores [out][in][kh][kw], ConvTranspose2d [in][out][kh][kw]
+                    ci, co, kh, kw = conv.weight.shape
+                    w = w.view(co, ci, kh, kw).permute(1, 0, 2, 3).contiguous()
+                conv.weight.copy_(w.view_as(conv.weight))
+                b = torch.from_numpy(l["bias"])
+                if bn is None:
+                    conv.bias.copy_(b)
+                else:
+                    bn.weight.fill_(1.0)
+                    bn.bias.copy_(b)
+                    bn.running_mean.zero_()
+                    bn.running_var.fill_(1.0)
+                    bn.eps = 0.0
+        self._dirty = True
+        return self
+
     # ---- execution ---------------------------------------------------------------------------
     def context(self, device, H, W, batch):
         """The yf_ctx serving (device, H, W); grown (re-created) when a larger batch arrives."""
