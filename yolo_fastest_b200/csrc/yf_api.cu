@@ -153,7 +153,7 @@ struct yf_ctx {
     int32_t* p_order = nullptr;
     unsigned char* p_alive = nullptr;
     // double-buffered asynchronous host path (yf_detect_submit_u8 / yf_detect_wait)
-    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_back = nullptr;      // H2D of inputs / kernels / D2H of results
     cudaStream_t s_cap = nullptr;                       // graphs are captured here (the caller's stream may be the legacy stream, which cannot capture)
     unsigned char* sl_u8[2] = {nullptr, nullptr};
     yf_det* sl_out[2] = {nullptr, nullptr};
@@ -1077,12 +1077,12 @@ extern "C" void yf_destroy(yf_ctx* ctx) {
     for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);
     if (ctx->s_cap) cudaStreamDestroy(ctx->s_cap);
     if (ctx->s_copy) {
-        cudaStreamSynchronize(ctx->s_copy); cudaStreamSynchronize(ctx->s_comp);
+        cudaStreamSynchronize(ctx->s_copy); cudaStreamSynchronize(ctx->s_comp); cudaStreamSynchronize(ctx->s_back);
         for (int i = 0; i < 2; ++i) {
             cudaFree(ctx->sl_u8[i]); cudaFree(ctx->sl_out[i]); cudaFree(ctx->sl_counts[i]); cudaFree(ctx->sl_status[i]);
             cudaEventDestroy(ctx->sl_in[i]); cudaEventDestroy(ctx->sl_free[i]); cudaEventDestroy(ctx->sl_done[i]);
         }
-        cudaStreamDestroy(ctx->s_copy); cudaStreamDestroy(ctx->s_comp);
+        cudaStreamDestroy(ctx->s_copy); cudaStreamDestroy(ctx->s_comp); cudaStreamDestroy(ctx->s_back);
     }
     delete ctx;
 }
@@ -1513,6 +1513,7 @@ static int slots_init(yf_ctx* ctx) {
     if (ctx->s_copy) return YF_OK;
     CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->s_back, cudaStreamNonBlocking));
     const size_t npx = (size_t)ctx->max_batch * ctx->in_ch * ctx->H * ctx->W;
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&ctx->sl_u8[i], npx));
@@ -1562,6 +1563,7 @@ static int submit_impl(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, con
     CU(cudaMemcpyAsync(ctx->sl_u8[slot], u8_host, npx, cudaMemcpyHostToDevice, ctx->s_copy));
     CU(cudaEventRecord(ctx->sl_in[slot], ctx->s_copy));
     CU(cudaStreamWaitEvent(ctx->s_comp, ctx->sl_in[slot], 0));
+    if (ctx->sl_used[slot]) CU(cudaStreamWaitEvent(ctx->s_comp, ctx->sl_done[slot], 0));   // the slot's previous results have left its buffers
     if (out_on_device) {    // results go straight into the caller's device buffers (e.g. to be gathered with NCCL)
         rc = detect_impl(ctx, ctx->sl_u8[slot], true, B, p, out_host, counts_host, status_host ? status_host : ctx->sl_status[slot], ctx->s_comp);
         if (rc) return rc;
@@ -1570,11 +1572,13 @@ static int submit_impl(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, con
         rc = detect_fixed(ctx, ctx->sl_u8[slot], true, B, p, ctx->sl_out[slot], ctx->sl_counts[slot], ctx->sl_status[slot], ctx->s_comp);
         if (rc) return rc;
         CU(cudaEventRecord(ctx->sl_free[slot], ctx->s_comp));
-        CU(cudaMemcpyAsync(out_host, ctx->sl_out[slot], sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, ctx->s_comp));
-        CU(cudaMemcpyAsync(counts_host, ctx->sl_counts[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_comp));
-        if (status_host) CU(cudaMemcpyAsync(status_host, ctx->sl_status[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_comp));
+        // the results travel back on their own stream, so the next batch's kernels start right behind this batch's
+        CU(cudaStreamWaitEvent(ctx->s_back, ctx->sl_free[slot], 0));
+        CU(cudaMemcpyAsync(out_host, ctx->sl_out[slot], sizeof(yf_det) * (size_t)B * p->max_det, cudaMemcpyDeviceToHost, ctx->s_back));
+        CU(cudaMemcpyAsync(counts_host, ctx->sl_counts[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_back));
+        if (status_host) CU(cudaMemcpyAsync(status_host, ctx->sl_status[slot], sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->s_back));
     }
-    CU(cudaEventRecord(ctx->sl_done[slot], ctx->s_comp));
+    CU(cudaEventRecord(ctx->sl_done[slot], out_on_device ? ctx->s_comp : ctx->s_back));
     ctx->sl_used[slot] = true;
     return YF_OK;
 }
