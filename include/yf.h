@@ -62,7 +62,8 @@ enum { YF_MODE_DETECT = 0,   /* src/detect.py:41-84,155-169 */
 /* ---- lifecycle -------------------------------------------------------------------------- */
 
 /* Replaces YoloFastest(io_params).to(device) (yolo_fastest.py:70-148; detect.py:89).
- * in_ch must be 1 (io_params["input_channel"], _config.py:10); H and W multiples of 32
+ * in_ch is 1 (io_params["input_channel"], _config.py:10: the shipped models) or 3 (colour input, yolo_fastest.py:73,78: planes
+ * in the order the reference feeds them, i.e. R, G, B after detect.py:121); H and W multiples of 32
  * (_config.py:11).  Head shapes follow: large = [B, A*(5+nc), H/16, W/16], small = [.., H/32, W/32]. */
 int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors,
               int max_batch, int H, int W);

@@ -45,6 +45,7 @@ def test_weight_count_matches_packer():
         bn = sum(mod.weight.numel() for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d))
         assert blob.size == n_params - bn
     assert yf.lib().yf_weight_count(0, 3, 3) < 0
+    assert yf.lib().yf_weight_count(3, 3, 3) == yf.lib().yf_weight_count(1, 3, 3) + 2 * 72      # conv0 [8][3][3][3] vs [8][1][3][3]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -66,7 +67,7 @@ def test_fails_loudly_without_gpu():
 def test_create_rejects_bad_arguments():
     h = C.c_void_p()
     l = yf.lib()
-    assert l.yf_create(C.byref(h), 0, 3, 3, 3, 1, 256, 320) == -1       # in_ch != 1
+    assert l.yf_create(C.byref(h), 0, 2, 3, 3, 1, 256, 320) == -1       # in_ch is 1 or 3
     assert b"in_ch" in l.yf_last_error(None)
     assert l.yf_create(C.byref(h), 0, 1, 3, 3, 1, 250, 320) == -1       # not a multiple of 32
     assert l.yf_create(C.byref(h), 0, 1, 3, 9, 1, 256, 320) == -1       # too many anchors

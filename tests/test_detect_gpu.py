@@ -176,3 +176,30 @@ def test_ncnn_weight_source(gold):
     hl, hs = det.model(x.cuda())
     for got_h, ref_h in ((hl.cpu(), rl), (hs.cpu(), rs)):
         assert float((got_h - ref_h).abs().max()) <= 1e-4 * float(ref_h.abs().max())
+
+
+def test_three_channel_detect_u8_equals_float(gold, tmp_path):
+    """3-channel network through Detect_YOLO: uint8 RGB planes [B, 3, H, W] with the normalisation fused into the stem give the
+    detections of the normalised fp32 batch, and those of the oracle."""
+    from test_forward_gpu import _three_channel_sd
+    sd = _three_channel_sd(gold)
+    path = str(tmp_path / "rgb.pth")
+    torch.save(sd, path)
+    cfg = yf.config_for("256x320")
+    cfg["io_params"]["input_channel"] = 3
+    cfg["io_params"]["input_shape"] = [256, 320, 3]
+    cfg["io_params"]["conf_thre"] = 0.3
+    det = yf.Detect_YOLO(torch.device("cuda:0"), path, cfg, None)
+    g = gold.res["256x320"]
+    gray = g["u8"][:6]
+    u8 = np.stack([gray, np.roll(gray, 3, axis=2), np.roll(gray, 5, axis=1)], axis=1)          # [B, 3, H, W], channels differ
+    rows = det.detect_batch(u8, max_det=32)
+    x = ((torch.from_numpy(u8).float() - 128.0) / 255.0)
+    out, counts, status = det.detect_device(x.cuda(), max_det=32)
+    torch.cuda.synchronize()
+    assert [min(int(c), 32) for c in counts.cpu()] == [len(r) for r in rows] and sum(len(r) for r in rows) > 0
+    io = cfg["io_params"]
+    for i in range(len(u8)):
+        pred = O.forward(sd, x[i:i + 1])
+        want = O.detect_postprocess(pred, io["anchors"], io["input_shape"], io["conf_thre"], io["nms_thre"], io["num_anchors"], io["num_cls"])
+        _match([list(r) for r in want], rows[i])

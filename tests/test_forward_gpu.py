@@ -32,9 +32,11 @@ def _close(got, ref, what, rel=TOL):
 
 def _check_heads(m, sd, x, what, rel=TOL):
     """Two-sided criterion. (1) GPU vs the reference's fp32 result: within `rel` of the tensor scale.
-    (2) GPU vs the same network evaluated in float64: no further from exact arithmetic than 1.5x the
-    reference's own fp32 result is (measured: the reference is ~1.3e-5 of scale away from fp64 at 512x640,
-    tools/noise_floor.py) — i.e. the GPU path adds no error beyond the reference's fp32 noise floor."""
+    (2) GPU vs the same network evaluated in float64: within 1e-5 of the tensor scale of exact arithmetic (a tenth of the
+    tolerance; measured on the trained networks: 3.5e-6 .. 5.4e-6, the reference's own fp32 result sits 1e-6 .. 1.3e-5 away,
+    tools/noise_floor.py, tools/ch3_probe.py), or - on the ill-conditioned stress networks, where fp32 itself is further away - no
+    further than 1.5x the reference's own distance. The GPU's extra distance on trained networks is the truncating accumulation
+    of the tensor core, bounded by keeping the accumulation chains short."""
     sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
     ref32 = O.forward(sd, x)
     ref64 = O.forward(sd64, x.double())
@@ -46,7 +48,8 @@ def _check_heads(m, sd, x, what, rel=TOL):
         scale = ref64[h].abs().max().item()
         e_ref = (ref32[h].double() - ref64[h]).abs().max().item()
         e_gpu = (g.double() - ref64[h]).abs().max().item()
-        assert e_gpu <= 1.5 * e_ref + 2e-6 * scale, "%s %s: gpu is %.3g from fp64, the reference only %.3g" % (what, name, e_gpu, e_ref)
+        assert e_gpu <= max(1.5 * e_ref + 2e-6 * scale, 1e-5 * scale), \
+            "%s %s: gpu is %.3g from fp64 (scale %.3g), the reference only %.3g" % (what, name, e_gpu, scale, e_ref)
     return got, ref32
 
 
@@ -160,3 +163,26 @@ def test_ffma_variant():
                                env=dict(os.environ, YF_B200_LIB=lib), capture_output=True, text=True, timeout=600)
             assert r.returncode == 0, name + "\n" + r.stdout[-3000:] + r.stderr[-2000:]
             assert "res3_4" in r.stdout and "res4_2" in r.stdout
+
+
+def _three_channel_sd(gold):
+    """The shipped 256x320 network with its first convolution widened to 3 input channels: the trained gray kernel
+    spread over the channels with unequal weights plus a seeded perturbation, so every channel matters and the net stays trained-like."""
+    sd = dict(gold.sd("yolo_fastest_256x320"))
+    w = sd["conv0.0.weight"]
+    gen = torch.Generator().manual_seed(5)
+    sd["conv0.0.weight"] = torch.cat([w * c for c in (0.5, 0.3, 0.2)], 1) + 0.05 * w.abs().mean() * torch.randn((8, 3, 3, 3), generator=gen)
+    return sd
+
+
+@pytest.mark.parametrize("H,W,B", [(256, 320, 3), (96, 352, 2), (32, 32, 1), (512, 640, 1)])
+def test_three_channel_input(gold, H, W, B):
+    """in_ch = 3 (`io_params["input_channel"]`, yolo_fastest.py:73,78): the stem's colour instantiation against the oracle."""
+    sd = _three_channel_sd(gold)
+    m = yf.YoloFastest({"num_cls": 3, "input_channel": 3, "num_anchors": 3})
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = (torch.randint(0, 256, (B, 3, H, W), generator=torch.Generator().manual_seed(29)).float() - 128.0) / 255.0
+    _check_heads(m, sd, x, "3-channel %dx%d" % (H, W))
+    with pytest.raises(yf.YfError):
+        m(x[:, :1].cuda())                          # a gray batch is rejected, not broadcast

@@ -194,6 +194,7 @@ struct yf_ctx {
 #define YF_CFGSTEM StemCfg<8, 80, 256, 2>
 #endif
 using CfgStem = YF_CFGSTEM;
+using CfgStem3 = StemCfg<8, 40, 256, 2, 3>;          // 3-channel (colour) input: smaller tile, the raw rectangle is three planes
 #ifndef YF_CFGRES1
 #define YF_CFGRES1 IrbCfg<4, 8, 4, 3, 1, 8, 80, 8, 8, 4, 8, 256, 3, true, true, false, false>
 #endif
@@ -350,6 +351,7 @@ int occ_of(K kernel, int nt, int smem) {
 }
 template <class C> int occ_irb() { return occ_of(irb_kernel<C>, C::NT, C::SMEM_BYTES); }
 int occ_stem() { return occ_of(stem_kernel<CfgStem, false>, CfgStem::NT, CfgStem::SMEM_BYTES); }
+int occ_stem3() { return occ_of(stem_kernel<CfgStem3, false>, CfgStem3::NT, CfgStem3::SMEM_BYTES); }
 int occ_dense() { return occ_of(dense_kernel<CfgDense>, CfgDense::NT, CfgDense::SMEM_BYTES); }
 int occ_upcat() { return occ_of(upcat_kernel<CfgUpCat>, CfgUpCat::NT, CfgUpCat::SMEM_BYTES); }
 int occ_upcat_tc() { return occ_of(upcat_tc_kernel<CfgUpCatTc>, CfgUpCatTc::NT, CfgUpCatTc::SMEM_BYTES); }
@@ -411,9 +413,9 @@ cudaError_t init_irbtc() { return cudaFuncSetAttribute(irbtc_kernel<C>, cudaFunc
 template <class C>
 cudaError_t init_irb() { return cudaFuncSetAttribute(irb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
 
+template <class C>
 void launch_stem(const GroupArgs& g, const void* xin, bool u8in, int B, cudaStream_t st) {
-    using C = CfgStem;
-    using G = C::G;
+    using G = typename C::G;
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;
@@ -688,14 +690,15 @@ int64_t pack_irbtc(std::vector<float>& out, const Folded& f, const std::string& 
     return off;
 }
 
+template <class C>
 int64_t pack_stem(std::vector<float>& out, const Folded& f) {
-    using C = CfgStem;
     pad4(out);
     const int64_t off = (int64_t)out.size();
     out.resize(off + C::WFLOATS, 0.f);
     float* o = out.data() + off;
-    for (int c = 0; c < 8; ++c)
-        for (int t = 0; t < 9; ++t) o[C::OFF_W0 + t * 8 + c] = f.w("conv0")[c * 9 + t];
+    for (int c = 0; c < 8; ++c)                          // conv0 weight [8][CIN][3][3] -> [ci][tap][c]
+        for (int ci = 0; ci < C::CIN; ++ci)
+            for (int t = 0; t < 9; ++t) o[C::OFF_W0 + (ci * 9 + t) * 8 + c] = f.w("conv0")[(c * C::CIN + ci) * 9 + t];
     for (int c = 0; c < 8; ++c) o[C::OFF_B0 + c] = f.b("conv0")[c];
     for (int m = 0; m < 8; ++m)
         for (int k = 0; k < 8; ++k) o[C::OFF_W1 + k * 8 + m] = f.w("conv1_2")[m * 8 + k];
@@ -928,7 +931,9 @@ static void build_plan(yf_ctx* ctx) {
         G.push_back(g);
     };
     {
-        Group g{}; g.name = "conv1_4"; g.launch = &launch_stem; g.occupancy = &occ_stem; g.out_ch = 4;
+        Group g{}; g.name = "conv1_4"; g.out_ch = 4;
+        if (ctx->in_ch == 3) { g.launch = &launch_stem<CfgStem3>; g.occupancy = &occ_stem3; }
+        else { g.launch = &launch_stem<CfgStem>; g.occupancy = &occ_stem; }
         g.a.Hin = H; g.a.Win = W; g.a.Hout = H / 2; g.a.Wout = W / 2;
         g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
@@ -1021,7 +1026,7 @@ static void set_sm_count(yf_ctx* ctx) {
 extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors, int max_batch, int H, int W) {
     if (!out) { set_err(nullptr, "out is null"); return YF_ERR_ARG; }
     *out = nullptr;
-    if (in_ch != 1) { set_err(nullptr, "in_ch=%d unsupported: the shipped models are single-channel (_config.py:10)", in_ch); return YF_ERR_ARG; }
+    if (in_ch != 1 && in_ch != 3) { set_err(nullptr, "in_ch=%d unsupported: 1 (the shipped models, _config.py:10) or 3 (colour input)", in_ch); return YF_ERR_ARG; }
     if (num_cls < 1 || num_cls > POST_MAX_CLS || num_anchors < 1 || num_anchors > YF_MAX_ANCHORS || max_batch < 1) {
         set_err(nullptr, "bad num_cls/num_anchors/max_batch (%d, %d, %d)", num_cls, num_anchors, max_batch);
         return YF_ERR_ARG;
@@ -1044,6 +1049,8 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
     cudaError_t ie[] = {
         cudaFuncSetAttribute(stem_kernel<CfgStem, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem::SMEM_BYTES),
         cudaFuncSetAttribute(stem_kernel<CfgStem, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem::SMEM_BYTES),
+        cudaFuncSetAttribute(stem_kernel<CfgStem3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem3::SMEM_BYTES),
+        cudaFuncSetAttribute(stem_kernel<CfgStem3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem3::SMEM_BYTES),
         cudaFuncSetAttribute(dense_kernel<CfgDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDense::SMEM_BYTES),
         cudaFuncSetAttribute(dense_tc_kernel<CfgDenseTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDenseTc::SMEM_BYTES),
         cudaFuncSetAttribute(pw_kernel<CfgPw52>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPw52::SMEM_BYTES),
@@ -1104,7 +1111,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
         using C = decltype(tag);
         offs.push_back(pack_irb<C>(P, f, n + ".conv1", n + ".conv2", n + ".conv3", "", 0));
     };
-    offs.push_back(pack_stem(P, f));
+    offs.push_back(ctx->in_ch == 3 ? pack_stem<CfgStem3>(P, f) : pack_stem<CfgStem>(P, f));
 #if YF_USE_THIN
     offs.push_back(pack_thin<CfgRes1Thin>(P, f, "res1_1.conv1", "res1_1.conv2", "res1_1.conv3"));
 #else

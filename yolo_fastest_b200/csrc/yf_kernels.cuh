@@ -607,20 +607,21 @@ irb_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict
 // ---------------------------------------------------------------------------------------------
 // Stem group: conv0 (dense 3x3 s2, in_ch=1 -> 8, ReLU) -> conv1_2 (1x1 8->8 ReLU) -> conv1_3 (dw3x3 ReLU)
 // -> conv1_4 (1x1 8->4 linear)   (yolo_fastest.py:78-82,151-154).  Input [B,1,H,W], output [B,4,H/2,W/2].
-// Packed weights: [W0: 9*8 ([tap][c])][b0: 8][W1: 8*8 ([k][m])][b1: 8][Wd: 8*9][bd: 8][W2: 8*4 ([m][n])][b2: 4]
+// Packed weights: [W0: CIN*9*8 ([ci][tap][c])][b0: 8][W1: 8*8 ([k][m])][b1: 8][Wd: 8*9][bd: 8][W2: 8*4 ([m][n])][b2: 4]
 // With U8IN the input is uint8 and (x-128)/255 is applied on load (detect.py:123-124).
 // ---------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int NT_, int MINB_>
+template <int TH_, int TW_, int NT_, int MINB_, int CIN_ = 1>
 struct StemCfg {
-    static constexpr int NT = NT_, MINB = MINB_;
+    static constexpr int NT = NT_, MINB = MINB_, CIN = CIN_;          // CIN: image channels (1 = the shipped models, 3 = colour input)
     using G = Geo<3, 1, TH_, TW_>;
     static constexpr int RH = 2 * G::IH + 1;          // raw input rows feeding the conv0 halo tile
     static constexpr int RW = 2 * G::IWS + 1;         // raw input columns
     static constexpr int REW = G::IWS + 4;            // raw rows are stored parity-split: [even cols (REW) | odd cols (IWS)]
     static constexpr int RWS = REW + G::IWS;
-    static constexpr int OFF_W0 = 0, OFF_B0 = 72, OFF_W1 = 80, OFF_B1 = 144, OFF_WD = 152, OFF_BD = 224, OFF_W2 = 232, OFF_B2 = 264;
-    static constexpr int WFLOATS = 268;
-    static constexpr int RS = RH * RWS;
+    static constexpr int OFF_W0 = 0, OFF_B0 = 72 * CIN, OFF_W1 = OFF_B0 + 8, OFF_B1 = OFF_W1 + 64, OFF_WD = OFF_B1 + 8, OFF_BD = OFF_WD + 72,
+                         OFF_W2 = OFF_BD + 8, OFF_B2 = OFF_W2 + 32;
+    static constexpr int WFLOATS = OFF_B2 + 4;
+    static constexpr int RS1 = RH * RWS, RS = CIN * RS1;              // raw rectangle of one channel / of all channels
     static constexpr int NPRE = cdiv(RS, NT_);
     static constexpr int XS = 8 * G::IPIX, ES = 8 * G::IPIX, DS = 8 * G::OPIX;
     static constexpr int WPAD = rup(WFLOATS, 4);
@@ -656,12 +657,13 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
 #pragma unroll
         for (int k = 0; k < NPRE; ++k) {
             const int idx = threadIdx.x + k * NT;
-            const int r = idx / C::RWS, jj = idx - r * C::RWS;
+            const int ci = C::CIN == 1 ? 0 : idx / C::RS1, i1 = idx - ci * C::RS1;
+            const int r = i1 / C::RWS, jj = i1 - r * C::RWS;
             const int j = jj < C::REW ? 2 * jj : 2 * (jj - C::REW) + 1;     // raw column held at split position jj
             const int gy = ry0 + r, gx = rx0 + j;
             float v = 0.f;
             if (idx < C::RS && j < C::RW && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win) {
-                const size_t off = ((size_t)b * Hin + gy) * Win + gx;
+                const size_t off = (((size_t)b * C::CIN + ci) * Hin + gy) * Win + gx;
                 if (U8IN) v = Lut[__ldg(reinterpret_cast<const unsigned char*>(xin) + off)];
                 else v = __ldg(reinterpret_cast<const float*>(xin) + off);
             }
@@ -698,9 +700,11 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
 #pragma unroll
                 for (int i = 0; i < 4; ++i) a[c][i] = Ws[C::OFF_B0 + c];
 #pragma unroll
+            for (int ci = 0; ci < C::CIN; ++ci)
+#pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
                 float v[9];   // raw columns 2*j0 .. 2*j0+8 of this row: v[2i+dx] feeds output i, tap dx
-                const float* rp = Rs + (2 * r + dy) * C::RWS + j0;
+                const float* rp = Rs + ci * C::RS1 + (2 * r + dy) * C::RWS + j0;
                 {
                     const float4 a = ld4(rp), b = ld4(rp + 4), c = ld4(rp + C::REW);
                     v[0] = a.x; v[2] = a.y; v[4] = a.z; v[6] = a.w; v[8] = b.x;
@@ -708,8 +712,8 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
                 }
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const float4 wa = ld4(W0 + (dy * 3 + dx) * 8);
-                    const float4 wb = ld4(W0 + (dy * 3 + dx) * 8 + 4);
+                    const float4 wa = ld4(W0 + (ci * 9 + dy * 3 + dx) * 8);
+                    const float4 wb = ld4(W0 + (ci * 9 + dy * 3 + dx) * 8 + 4);
                     const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
                     for (int c = 0; c < 8; ++c)

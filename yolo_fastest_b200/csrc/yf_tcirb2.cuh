@@ -38,7 +38,11 @@ struct IrbTc2Cfg {
     static constexpr int SLOT = rup(cmax(2 * NA * MC, OFF_BD + MC), 32);
     static constexpr int OFF_B2 = STEPS * SLOT;
     static constexpr int WFLOATS = OFF_B2 + COUT;
-    static constexpr int TM_O = 0, TM_E = MT3 * COUTP, TCOLS = pow2_ge(TM_E + MT1 * NA);
+    // project accumulators per 128-pixel tile: [hi.hi of even chunks | hi.hi of odd chunks | both correction terms of all chunks].
+    // The tensor core accumulates with truncation, so the error of an accumulator grows with its MMA chain: the main term gets two
+    // short chains (CMID / 32 steps each) and never shares an accumulator with the small terms; the three are summed in the epilogue
+    static constexpr int NACC = 3;
+    static constexpr int TM_O = 0, TM_E = MT3 * NACC * COUTP, TCOLS = pow2_ge(TM_E + MT1 * NA);
     static constexpr int SMEM_FLOATS = 4 * DA1 + 2 * XA1 + 2 * ES1 + NWB * SLOT;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + 1024;
     static constexpr int NITEM_X = (CIN / 8) * G::IPIX;
@@ -125,7 +129,7 @@ irbtc2_kernel(const float* __restrict__ x, float* __restrict__ y, const float* _
                 }
                 umma_commit(&efull);
             };
-            auto gemm_b_chunk = [&](bool first) {         // O += D chunk . W2 chunk
+            auto gemm_b_chunk = [&](int k) {              // O += D chunk . W2 chunk (k = chunk index inside the tile)
                 const int b = d & 1;
                 mbar_wait(&dfull[b], (d >> 1) & 1);
                 const uint64_t wb = step_begin();
@@ -133,12 +137,15 @@ irbtc2_kernel(const float* __restrict__ x, float* __restrict__ y, const float* _
                 const uint64_t db = dd0 + (uint64_t)((uint32_t)(b * 2 * C::DA1 * 4) >> 4);
 #pragma unroll 1
                 for (int mt = 0; mt < C::MT3; ++mt) {
+                    const uint32_t o0 = tmem + C::TM_O + mt * C::NACC * C::COUTP;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
                         for (int kb = 0; kb < C::MC / 8; ++kb)
-                            umma_tf32(tmem + C::TM_O + mt * C::COUTP, db + (uint64_t)(mt * 256) + (uint64_t)(((pass == 2 ? C::DA1 : 0) + kb * C::KB3) * 4 / 16),
-                                      wb + (uint64_t)(((pass == 1 ? C::COUTP * C::MC : 0) * 4 + kb * 256) / 16), IDESC_B, (first && pass == 0 && kb == 0) ? 0u : 1u);
+                            umma_tf32(o0 + (pass == 0 ? (k & 1) : 2) * C::COUTP,
+                                      db + (uint64_t)(mt * 256) + (uint64_t)(((pass == 2 ? C::DA1 : 0) + kb * C::KB3) * 4 / 16),
+                                      wb + (uint64_t)(((pass == 1 ? C::COUTP * C::MC : 0) * 4 + kb * 256) / 16), IDESC_B,
+                                      (kb == 0 && ((pass == 0 && k < 2) || (pass == 1 && k == 0))) ? 0u : 1u);
                 }
                 umma_commit(&dfree[b]);
                 step_end();
@@ -153,7 +160,7 @@ irbtc2_kernel(const float* __restrict__ x, float* __restrict__ y, const float* _
                     if (eh > 0) mbar_wait(&efree, (eh - 1) & 1);               // the previous half of E has been read out of TMEM
                     gemm_a();
                     if (h == 0 && ti > 0) mbar_wait(&ofree, (ti - 1) & 1);     // the previous tile's output has been read out
-                    for (int c = 0; c < C::NMC; ++c) gemm_b_chunk(h == 0 && c == 0);
+                    for (int c = 0; c < C::NMC; ++c) gemm_b_chunk(h * C::NMC + c);
                 }
                 umma_commit(&ofull);
             }
@@ -267,8 +274,12 @@ irbtc2_kernel(const float* __restrict__ x, float* __restrict__ y, const float* _
                 const int pix = mt * 128 + quarter * 32 + lane;
                 const int oy = pix / G::TW, ox = pix - oy * G::TW;
                 const int gy = oy0 + oy, gx = ox0 + ox;
-                float v[16];
-                tmem_ld16(tmem + lane_base + C::TM_O + mt * C::COUTP + c0, v);
+                float v[16], v1[16], v2[16];
+                tmem_ld16(tmem + lane_base + C::TM_O + mt * C::NACC * C::COUTP + c0, v);
+                tmem_ld16(tmem + lane_base + C::TM_O + mt * C::NACC * C::COUTP + C::COUTP + c0, v1);
+                tmem_ld16(tmem + lane_base + C::TM_O + mt * C::NACC * C::COUTP + 2 * C::COUTP + c0, v2);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = (v[i] + v1[i]) + v2[i];
                 if (pix < G::OPIX && gy < H && gx < W) {
                     const size_t o = ((size_t)tb * C::COUT + c0) * plane + (size_t)gy * W + gx;
 #pragma unroll

@@ -165,6 +165,9 @@ class Detect_YOLO:
 
     # ---- host-side image handling (unchanged semantics, detect.py:107-139) ------------------------
     def _load_gray(self, img_path):
+        """imread -> (gray) -> resize: the uint8 network input, [H, W] for the single-channel models, [3, H, W] in RGB plane
+        order for 3-channel ones (detect.py:107-122: cvtColor only when the network is single-channel, then `[:, :, ::-1]` and
+        HWC -> CHW)."""
         import cv2
         ori_img = cv2.imread(img_path)
         if self.input_shape[2] == 1 and self.origin_img_shape[2] != 1:
@@ -173,14 +176,16 @@ class Detect_YOLO:
             img = ori_img
         if list(self.input_shape[0:2]) != list(self.origin_img_shape[0:2]):
             img = cv2.resize(img, (self.input_shape[1], self.input_shape[0]))
-        if img.ndim != 2:
-            raise _lib.YfError("the B200 path serves the single-channel models (input_shape[2] == 1)")
-        return np.ascontiguousarray(img), ori_img
+        if self.input_shape[2] == 1:
+            if img.ndim != 2:
+                raise _lib.YfError("a single-channel network needs gray input: origin_img_shape[2] must not be 1 for 3-channel files")
+            return np.ascontiguousarray(img), ori_img
+        return np.ascontiguousarray(img[:, :, ::-1].transpose(2, 0, 1)), ori_img
 
     def pre_process(self, img_path):
-        """imread -> gray -> resize -> (x - 128) / 255 -> [1, 1, H, W] on the device (detect.py:107-129)."""
+        """imread -> gray -> resize -> (x - 128) / 255 -> [1, C, H, W] on the device (detect.py:107-129)."""
         u8, ori_img = self._load_gray(img_path)
-        img = torch.from_numpy(u8[None]).to(self.device).float()
+        img = torch.from_numpy(u8[None] if u8.ndim == 2 else u8).to(self.device).float()
         img = (img - 128.0) / 255.0
         return img.unsqueeze(0), ori_img
 
@@ -252,7 +257,8 @@ class Detect_YOLO:
 
     # ---- batched detection through the C ABI with host buffers -----------------------------------------
     def detect_batch(self, u8_batch, max_det=64, raw=False):
-        """uint8 gray images [B, H, W] (host numpy array or host torch tensor, network input size) -> per-image rows.
+        """uint8 images [B, H, W] (gray) or [B, 3, H, W] (RGB planes, 3-channel networks), host numpy array or host torch
+        tensor at the network input size -> per-image rows.
 
         One yf_detect_host_u8 call: H2D copy of the bytes, fused normalisation + forward + decode +
         NMS, D2H copy of the fixed-capacity result slab.  This is the end-to-end call bench.py times."""
@@ -260,13 +266,14 @@ class Detect_YOLO:
             and u8_batch.is_contiguous()
         if not direct:
             u8_batch = np.ascontiguousarray(u8_batch, dtype=np.uint8)
-        B, H, W = u8_batch.shape
-        if [H, W] != list(self.input_shape[0:2]):
-            raise _lib.YfError("images are %dx%d, the network input is %s" % (H, W, self.input_shape[0:2]))
+        B, H, W = u8_batch.shape[0], u8_batch.shape[-2], u8_batch.shape[-1]
+        chans = 1 if u8_batch.ndim == 3 else u8_batch.shape[1]
+        if [H, W] != list(self.input_shape[0:2]) or chans != self.input_shape[2] or u8_batch.ndim not in (3, 4):
+            raise _lib.YfError("images are %s, the network input is %s" % (tuple(u8_batch.shape[1:]), self.input_shape))
         ctx = self.model.context(self.device, H, W, B)
         key = (B, max_det)
         if key not in self._pinned:
-            self._pinned = {key: (torch.empty((B, H, W), dtype=torch.uint8).pin_memory(),
+            self._pinned = {key: (torch.empty((B, chans, H, W), dtype=torch.uint8).pin_memory(),
                                   torch.empty((B, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8).pin_memory(),
                                   torch.empty((B,), dtype=torch.int32).pin_memory(),
                                   torch.empty((B,), dtype=torch.int32).pin_memory())}
@@ -274,7 +281,7 @@ class Detect_YOLO:
         if direct:
             pin_in = u8_batch            # a host tensor (ideally pinned) is handed to the C ABI as is
         else:
-            pin_in.numpy()[...] = u8_batch
+            pin_in.numpy()[...] = u8_batch.reshape(B, chans, H, W)
         p = self.post_process._params(_lib.MODE_DETECT, max_det)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
