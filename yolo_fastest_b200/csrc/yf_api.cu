@@ -726,7 +726,8 @@ int64_t pack_dense_tc(std::vector<float>& out, const Folded& f) {
             for (int n = 0; n < 24; ++n)
                 for (int kl = 0; kl < 8; ++kl) put_kmajor_split(blk, blk + 32 * 8, n, kl, 8, w9[((n * 24 + cb * 8 + kl) * 3 + t / 3) * 3 + t % 3]);
         }
-    for (int i = 0; i < 96; ++i) o[C::OFF_W8 + i] = f.w("conv1_8")[i];          // [24][4]
+    for (int c = 0; c < 24; ++c)                                                // [24][4] -> [c / 4][k][c % 4]: one 128-bit load = 4 channels of one k
+        for (int k = 0; k < 4; ++k) o[C::OFF_W8 + (c / 4) * 16 + k * 4 + (c % 4)] = f.w("conv1_8")[c * 4 + k];
     for (int i = 0; i < 24; ++i) { o[C::OFF_B8 + i] = f.b("conv1_8")[i]; o[C::OFF_B9 + i] = f.b("conv1_9")[i]; }
     for (int j = 0; j < 8; ++j)
         for (int n = 0; n < 24; ++n) o[C::OFF_W21 + n * 8 + j] = f.w("conv2_1")[j * 24 + n];        // [8][24] -> transposed [24][8]

@@ -275,10 +275,10 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
 #pragma unroll 1
                 for (int cb = 0; cb < 3; ++cb, ++d) {
                     const int sl = d % C::NS;
-                    float4 w8r[4];                                   // conv1_8 weights / bias of this thread's 4 channels in this step
-                    float b8r[4];
+                    float4 w8k[4];                                   // conv1_8 weights of this thread's 4 channels in this step: w8k[k] = the 4 channels' k-th weight
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) { w8r[cc] = ld4(Wr + C::OFF_W8 + (cb * 8 + cg * 4 + cc) * 4); b8r[cc] = Wr[C::OFF_B8 + cb * 8 + cg * 4 + cc]; }
+                    for (int k = 0; k < 4; ++k) w8k[k] = ld4(Wr + C::OFF_W8 + (cb * 2 + cg) * 16 + k * 4);
+                    const float4 b8v = ld4(Wr + C::OFF_B8 + cb * 8 + cg * 4);
                     if (d >= C::NS) mbar_wait(&dfree[sl], ((d / C::NS) - 1) & 1);
                     if (tid == 0 && cb == 0) DTRACE(ti, 6);
                     float* Eh = Ebuf + sl * C::SLOT;
@@ -286,13 +286,15 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
                     for (int i = 0; i < C::IPT; ++i) {
                         if (tl + i * C::NTH < C::NPIX_IN) {
                             float hi[4], lo[4];
+                            float ev[4] = {b8v.x, b8v.y, b8v.z, b8v.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {             // packed FMAs over channel pairs (fmaf rounding per lane), k ascending like the scalar loop
+                                ffma2(w8k[k].x, w8k[k].y, xv[i][k], ev[0], ev[1]);
+                                ffma2(w8k[k].z, w8k[k].w, xv[i][k], ev[2], ev[3]);
+                            }
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) {
-                                float e = fmaf(w8r[cc].x, xv[i][0], b8r[cc]);
-                                e = fmaf(w8r[cc].y, xv[i][1], e);
-                                e = fmaf(w8r[cc].z, xv[i][2], e);
-                                e = fmaf(w8r[cc].w, xv[i][3], e);
-                                e = in[i] ? fmaxf(e, 0.f) : 0.f;      // conv1_9 zero-pads ITS input, the activation
+                                const float e = in[i] ? fmaxf(ev[cc], 0.f) : 0.f;      // conv1_9 zero-pads ITS input, the activation
                                 hi[cc] = tf32_hi(e);
                                 lo[cc] = e - hi[cc];
                             }
