@@ -121,6 +121,13 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def dist_shard(n, rank, world):
+    """images of a job of n this rank takes (contiguous, ragged: yolo_fastest_b200.dist.shard_range)"""
+    from yolo_fastest_b200.dist import shard_range
+    lo, hi = shard_range(n, rank, world)
+    return hi - lo
+
+
 def synthetic_u8(B, H, W, seed):
     """Seeded uniform uint8 pixels (SURVEY.md §8d inputs 2-4)."""
     g = torch.Generator().manual_seed(seed)
@@ -182,6 +189,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", default="512x640", choices=["512x640", "256x320"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: a fixed job of this many images per step split over the GPUs (BASELINE config 4: 1024); "
+                         "default 0 = weak scaling with --batch images per GPU")
     ap.add_argument("--max-det", type=int, default=64)
     ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,10 +226,12 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     B = args.batch
+    if args.global_batch:
+        B = dist_shard(args.global_batch, rank, world)
     det = Detect_YOLO(dev, ckpt, cfg, None)
     u8 = synthetic_u8(B, H, W, 1000 + rank).pin_memory()
     x_dev = ((u8.to(dev).float().unsqueeze(1) - 128.0) / 255.0).contiguous()      # resident input: 4*B*H*W bytes (> L2 at B=256)
-    n_total = B * world
+    n_total = args.global_batch if args.global_batch else B * world
 
     def barrier():
         if world > 1:
@@ -387,7 +399,7 @@ def main():
 
     line = {
         "metric": METRIC, "value": n_total * args.steps / (ms_max * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%dx%d synthetic uint8 images, batch %d per GPU, shipped %s checkpoint, conf %.2f nms %.2f, max_det %d"
                    % (W, H, B, args.res, io["conf_thre"], io["nms_thre"], args.max_det),
