@@ -42,6 +42,10 @@ def test_folded_parameters_equal_the_checkpoint():
             w = w.reshape(co, -1, k, k).transpose(1, 0, 2, 3).ravel()
         raw += [w, l["bias"]]
     assert np.array_equal(a, np.concatenate(raw))
+    # a checkpoint loaded afterwards folds with the reference's eps again
+    m2 = _model().load_ncnn(PARAM, BIN)
+    m2.load_state_dict(torch.load(os.path.join(HERE, "golden", "weights", "yolo_fastest_256x320.pth"), map_location="cpu"))
+    assert np.array_equal(m2.folded_blob(), b)
 
 
 def test_rejects_foreign_files(tmp_path):

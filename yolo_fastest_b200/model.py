@@ -141,6 +141,9 @@ class YoloFastest(nn.Module):
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
+        for m in self.modules():                      # load_ncnn turns the BatchNorms into identities with eps 0: a checkpoint
+            if isinstance(m, nn.BatchNorm2d):         # brings real statistics back, and the reference's eps with them
+                m.eps = 1e-5
         self._dirty = True
         return out
 
