@@ -716,9 +716,9 @@ stem_kernel(const void* __restrict__ xin, float* __restrict__ y, const float* __
                     const float4 wb = ld4(W0 + (ci * 9 + dy * 3 + dx) * 8 + 4);
                     const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
+                    for (int c = 0; c < 8; c += 2)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) a[c][i] = fmaf(w8[c], v[2 * i + dx], a[c][i]);
+                        for (int i = 0; i < 4; ++i) ffma2(w8[c], w8[c + 1], v[2 * i + dx], a[c][i], a[c + 1][i]);
                 }
             }
 #pragma unroll
