@@ -155,6 +155,8 @@ struct yf_ctx {
     // double-buffered asynchronous host path (yf_detect_submit_u8 / yf_detect_wait)
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_back = nullptr;      // H2D of inputs / kernels / D2H of results
     cudaStream_t s_cap = nullptr;                       // graphs are captured here (the caller's stream may be the legacy stream, which cannot capture)
+    cudaStream_t s_side = nullptr;                      // small batches: the head_5 branch runs here, beside the upsample branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned char* sl_u8[2] = {nullptr, nullptr};
     yf_det* sl_out[2] = {nullptr, nullptr};
     int sl_out_cap[2] = {0, 0};
@@ -1084,6 +1086,9 @@ extern "C" void yf_destroy(yf_ctx* ctx) {
     cudaFree(ctx->p_alive); cudaFree(ctx->n_alive); cudaFree(ctx->prep_tab); cudaFree(ctx->d_bgr);
     for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);
     if (ctx->s_cap) cudaStreamDestroy(ctx->s_cap);
+    if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->s_copy) {
         cudaStreamSynchronize(ctx->s_copy); cudaStreamSynchronize(ctx->s_comp); cudaStreamSynchronize(ctx->s_back);
         for (int i = 0; i < 2; ++i) {
@@ -1175,16 +1180,33 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+static const int kForkMaxBatch = 16;
 static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* head_large, float* head_small, cudaStream_t st) {
     if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
     if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
     if (!x || !head_large || !head_small) { set_err(&ctx->err, "null tensor pointer"); return YF_ERR_ARG; }
     static const bool debug_sync = getenv("YF_DEBUG_SYNC") != nullptr;
+    // Small batches leave most SMs idle in the low-resolution groups, so the two head branches (yolo_fastest.py:203-216: conv5_3..head_5
+    // and deconv5_1..head_4, both fed by conv5_2) run side by side: fork after conv5_2, join before the caller's next work. Large
+    // batches fill the GPU with every kernel and stay on one stream.
+    static const bool no_fork = getenv("YF_NO_FORK") != nullptr;
+    const bool fork = B <= kForkMaxBatch && !no_fork;
+    if (fork && !ctx->s_side) {
+        CU(cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
     for (Group& g : ctx->groups) {
         GroupArgs a = g.a;
-        if (!strcmp(g.name, "head_5")) a.y = head_small;
+        const bool h5 = !strcmp(g.name, "head_5"), side = fork && (h5 || !strcmp(g.name, "conv5_4"));
+        if (h5) a.y = head_small;
         if (!strcmp(g.name, "head_4")) a.y = head_large;
-        g.launch(a, x, u8in, B, st);
+        if (side && !h5) {
+            CU(cudaEventRecord(ctx->ev_fork, st));
+            CU(cudaStreamWaitEvent(ctx->s_side, ctx->ev_fork, 0));
+        }
+        g.launch(a, x, u8in, B, side ? ctx->s_side : st);
+        if (side && h5) CU(cudaEventRecord(ctx->ev_join, ctx->s_side));
         ctx->launches++;
         if (debug_sync) {   // YF_DEBUG_SYNC=1: attribute a device fault to the group that raised it
             cudaError_t e = cudaStreamSynchronize(st);
@@ -1195,6 +1217,7 @@ static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* hea
             }
         }
     }
+    if (fork) CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU(cudaGetLastError());
     return YF_OK;
 }
