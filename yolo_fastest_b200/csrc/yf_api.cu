@@ -331,6 +331,15 @@ using CfgDenseTc = DenseTcCfg<12>;
 #define YF_CFGRES5_TC IrbTc2Cfg<48, 224, 48, 8, 20, 2, 2, 10, true>
 #endif
 using CfgRes5Tc = YF_CFGRES5_TC;
+// Small-batch (latency) variants: the same kernels and the same packed weights on half-height tiles. At batch 1 the low-resolution
+// maps give a handful of tiles (res5: 2, res4: 8, res3: 16 of the throughput shape), i.e. most SMs idle while one tile's step chain
+// runs; halving the tile halves that chain. Chosen per launch when the throughput tiling would leave more than half of the SMs idle.
+using CfgRes5TcS = IrbTc2Cfg<48, 224, 48, 4, 20, 2, 2, 10, true>;
+using CfgRes4TcS = IrbTcCfg<24, 136, 24, 4, 20, 32, 4, 10, true, true>;
+using CfgRes3bTcS = IrbTcCfg<16, 96, 16, 4, 40, 32, 4, 10, true, YF_TC3_E1ALL>;
+using CfgRes5TcXS = IrbTc2Cfg<48, 224, 48, 2, 20, 2, 2, 10, true>;          // quarter height: when even the half-height tiles leave 3/4 of the SMs idle
+using CfgNeckL1TcS = DwPwTcCfg<96, 96, 5, 4, 40, 16, 4, 10, false>;
+using CfgNeckL2TcS = DwPwTcCfg<96, 32, 5, 4, 40, 16, 4, 10, false, true>;
 // the tensor-core upsample+concat kernel moves the skip tensor with 128-bit loads: it needs the 1/16-resolution map to be a
 // multiple of 4 wide and even in height (true for the shipped 512x640 / 256x320 models; 416x416 falls back to upcat_kernel)
 static bool upcat_on_tc(int H, int W) { return YF_USE_TC && ((W / 16) % 4 == 0) && ((H / 16) % 2 == 0); }
@@ -384,6 +393,12 @@ void launch_dwpwtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st
     const int grid = total < g.resident ? total : g.resident;
     dwpw_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total, g.headn > 0 ? g.headn : C::N);
 }
+template <class CB, class CS>
+void launch_dwpwtc_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
+    static_assert(CB::WFLOATS == CS::WFLOATS && CB::CB == CS::CB, "both tile shapes read the same packed weights");
+    const int big = B * cdiv(g.Wout, CB::G::TW) * cdiv(g.Hout, CB::G::TH);
+    if (2 * big <= g.nsm) launch_dwpwtc<CS>(g, x, u8, B, st); else launch_dwpwtc<CB>(g, x, u8, B, st);
+}
 template <class C> int occ_dwpwtc() { return occ_of(dwpw_tc_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
 cudaError_t init_dwpwtc() { return cudaFuncSetAttribute(dwpw_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
@@ -396,6 +411,14 @@ void launch_irbtc2(const GroupArgs& g, const void*, bool, int B, cudaStream_t st
     const int grid = total < g.resident ? total : g.resident;
     irbtc2_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
 }
+// big tiles unless they would occupy less than half of the SMs (small batches): then the half-height variant
+template <class CB, class CS>
+void launch_irbtc2_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
+    const int big = B * cdiv(g.Wout, CB::G::TW) * cdiv(g.Hout, CB::G::TH);
+    if (4 * big <= g.nsm) launch_irbtc2<CfgRes5TcXS>(g, x, u8, B, st);
+    else if (2 * big <= g.nsm) launch_irbtc2<CS>(g, x, u8, B, st);
+    else launch_irbtc2<CB>(g, x, u8, B, st);
+}
 template <class C> int occ_irbtc2() { return occ_of(irbtc2_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
 cudaError_t init_irbtc2() { return cudaFuncSetAttribute(irbtc2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
@@ -407,6 +430,12 @@ void launch_irbtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st)
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;
     irbtc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+}
+template <class CB, class CS>
+void launch_irbtc_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
+    static_assert(CB::WFLOATS == CS::WFLOATS && CB::CB == CS::CB && CB::OFF_B2 == CS::OFF_B2, "both tile shapes read the same packed weights");
+    const int big = B * cdiv(g.Wout, CB::G::TW) * cdiv(g.Hout, CB::G::TH);
+    if (2 * big <= g.nsm) launch_irbtc<CS>(g, x, u8, B, st); else launch_irbtc<CB>(g, x, u8, B, st);
 }
 template <class C> int occ_irbtc() { return occ_of(irbtc_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
@@ -957,10 +986,10 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes3a>("res3_2", 8), 8, 8);
     chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
 #if YF_USE_TC
-    chain(make_irbtc<CfgRes3bTc>("res3_3", 16), 8, 8);
-    chain(make_irbtc<CfgRes3bTc>("res3_4", 16), 8, 8);
-    chain(make_irbtc<CfgRes3bTc>("res3_5", 16), 8, 8);
-    chain(make_irbtc<CfgRes3bTc>("res3_6", 16), 8, 8);
+    { Group g = make_irbtc<CfgRes3bTc>("res3_3", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS>; chain(g, 8, 8); }
+    { Group g = make_irbtc<CfgRes3bTc>("res3_4", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS>; chain(g, 8, 8); }
+    { Group g = make_irbtc<CfgRes3bTc>("res3_5", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS>; chain(g, 8, 8); }
+    { Group g = make_irbtc<CfgRes3bTc>("res3_6", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS>; chain(g, 8, 8); }
 #else
     chain(make_irb<CfgRes3b>("res3_3", 16), 8, 8);
     chain(make_irb<CfgRes3b>("res3_4", 16), 8, 8);
@@ -969,10 +998,10 @@ static void build_plan(yf_ctx* ctx) {
 #endif
     chain(make_irb<CfgDown3>("conv4_1", 24), 8, 16);
 #if YF_USE_TC
-    chain(make_irbtc<CfgRes4Tc>("res4_1", 24), 16, 16);
-    chain(make_irbtc<CfgRes4Tc>("res4_2", 24), 16, 16);
-    chain(make_irbtc<CfgRes4Tc>("res4_3", 24), 16, 16);
-    chain(make_irbtc<CfgRes4Tc>("res4_4", 24), 16, 16);
+    { Group g = make_irbtc<CfgRes4Tc>("res4_1", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
+    { Group g = make_irbtc<CfgRes4Tc>("res4_2", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
+    { Group g = make_irbtc<CfgRes4Tc>("res4_3", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
+    { Group g = make_irbtc<CfgRes4Tc>("res4_4", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
 #else
     chain(make_irb<CfgRes4>("res4_1", 24), 16, 16);
     chain(make_irb<CfgRes4>("res4_2", 24), 16, 16);
@@ -985,7 +1014,11 @@ static void build_plan(yf_ctx* ctx) {
         chain(g, 16, 32);
     }
 #if YF_RES5_TC
-    for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"}) chain(make_irbtc2<CfgRes5Tc>(n, 48), 32, 32);
+    for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"}) {
+        Group g = make_irbtc2<CfgRes5Tc>(n, 48);
+        g.launch = &launch_irbtc2_auto<CfgRes5Tc, CfgRes5TcS>;
+        chain(g, 32, 32);
+    }
 #else
     for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"}) chain(make_irb<CfgRes5>(n, 48), 32, 32);
 #endif
@@ -1007,12 +1040,13 @@ static void build_plan(yf_ctx* ctx) {
         hw(g, 16, 16); g.a.x = ctx->d_skip; g.a.x2 = conv5_2; g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
 #if YF_USE_TC
-    chain(make_dwpwtc<CfgNeckL1Tc>("conv4_1_3", 96), 16, 16);
+    { Group g = make_dwpwtc<CfgNeckL1Tc>("conv4_1_3", 96); g.launch = &launch_dwpwtc_auto<CfgNeckL1Tc, CfgNeckL1TcS>; chain(g, 16, 16); }
 #else
     chain(make_irb<CfgNeckL1>("conv4_1_3", 96), 16, 16);
 #endif
     {
         Group g = heads_on_tc(ctx->nout) ? make_dwpwtc<CfgNeckL2Tc>("head_4", 0) : make_irb<CfgNeckL2>("head_4", 0);   // y = caller's head_large
+        if (heads_on_tc(ctx->nout)) g.launch = &launch_dwpwtc_auto<CfgNeckL2Tc, CfgNeckL2TcS>;
         hw(g, 16, 16); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
 }
@@ -1064,7 +1098,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         init_thin<CfgRes1Thin>(),
 #endif
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
