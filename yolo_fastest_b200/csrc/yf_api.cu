@@ -338,6 +338,15 @@ using CfgRes5TcS = IrbTc2Cfg<48, 224, 48, 4, 20, 2, 2, 10, true>;
 using CfgRes4TcS = IrbTcCfg<24, 136, 24, 4, 20, 32, 4, 10, true, true>;
 using CfgRes3bTcS = IrbTcCfg<16, 96, 16, 4, 40, 32, 4, 10, true, YF_TC3_E1ALL>;
 using CfgRes5TcXS = IrbTc2Cfg<48, 224, 48, 2, 20, 2, 2, 10, true>;          // quarter height: when even the half-height tiles leave 3/4 of the SMs idle
+// Narrow-map variants: tile widths that fit the 1/16 and 1/32 maps of the 320x256 input (20 and 10 columns) - the throughput shapes
+// (40 / 20 columns wide) would compute half or three quarters of every tile outside the image. Same packed weights again.
+using CfgRes5TcN = IrbTc2Cfg<48, 224, 48, 8, 12, 2, 2, 10, true>;
+using CfgNeckS1TcN = DwPwTcCfg<96, 128, 5, 8, 12, 16, 4, 10, false>;
+using CfgNeckS2TcN = DwPwTcCfg<128, 32, 5, 8, 12, 16, 4, 10, false, true>;
+using CfgNeckL1TcN = DwPwTcCfg<96, 96, 5, 8, 20, 16, 4, 10, false>;
+using CfgNeckL2TcN = DwPwTcCfg<96, 32, 5, 8, 20, 16, 4, 10, false, true>;
+using CfgDown3N = IrbCfg<16, 96, 24, 3, 2, 4, 20, 16, 8, 8, 4, 256, 2, true, false, false, false>;
+using CfgDown4N = IrbCfg<24, 136, 48, 3, 2, 2, 12, 16, 8, 8, 2, 128, 4, true, false, true, true>;
 using CfgNeckL1TcS = DwPwTcCfg<96, 96, 5, 4, 40, 16, 4, 10, false>;
 using CfgNeckL2TcS = DwPwTcCfg<96, 32, 5, 4, 40, 16, 4, 10, false, true>;
 // the tensor-core upsample+concat kernel moves the skip tensor with 128-bit loads: it needs the 1/16-resolution map to be a
@@ -353,6 +362,11 @@ void launch_irb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;     // persistent: every CTA resident, loops over tiles
     irb_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.skip, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total, g.headn);
+}
+template <class CB, class CN>
+void launch_irb_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {      // CN: the narrow-map tile shape
+    static_assert(CB::CB == CN::CB && CB::OFF_B2 == CN::OFF_B2 && CB::MC == CN::MC, "both tile shapes read the same packed weights");
+    if (g.Wout <= CN::G::TW) launch_irb<CN>(g, x, u8, B, st); else launch_irb<CB>(g, x, u8, B, st);
 }
 template <class K>
 int occ_of(K kernel, int nt, int smem) {
@@ -393,11 +407,13 @@ void launch_dwpwtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st
     const int grid = total < g.resident ? total : g.resident;
     dwpw_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total, g.headn > 0 ? g.headn : C::N);
 }
-template <class CB, class CS>
-void launch_dwpwtc_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
-    static_assert(CB::WFLOATS == CS::WFLOATS && CB::CB == CS::CB, "both tile shapes read the same packed weights");
+template <class CB, class CS, class CN>
+void launch_dwpwtc_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {      // CS: small batches, CN: narrow maps
+    static_assert(CB::WFLOATS == CS::WFLOATS && CB::CB == CS::CB && CB::WFLOATS == CN::WFLOATS && CB::CB == CN::CB, "all tile shapes read the same packed weights");
     const int big = B * cdiv(g.Wout, CB::G::TW) * cdiv(g.Hout, CB::G::TH);
-    if (2 * big <= g.nsm) launch_dwpwtc<CS>(g, x, u8, B, st); else launch_dwpwtc<CB>(g, x, u8, B, st);
+    if (g.Wout <= CN::G::TW) launch_dwpwtc<CN>(g, x, u8, B, st);
+    else if (2 * big <= g.nsm) launch_dwpwtc<CS>(g, x, u8, B, st);
+    else launch_dwpwtc<CB>(g, x, u8, B, st);
 }
 template <class C> int occ_dwpwtc() { return occ_of(dwpw_tc_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
@@ -415,7 +431,8 @@ void launch_irbtc2(const GroupArgs& g, const void*, bool, int B, cudaStream_t st
 template <class CB, class CS>
 void launch_irbtc2_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
     const int big = B * cdiv(g.Wout, CB::G::TW) * cdiv(g.Hout, CB::G::TH);
-    if (4 * big <= g.nsm) launch_irbtc2<CfgRes5TcXS>(g, x, u8, B, st);
+    if (g.Wout <= CfgRes5TcN::G::TW) launch_irbtc2<CfgRes5TcN>(g, x, u8, B, st);
+    else if (4 * big <= g.nsm) launch_irbtc2<CfgRes5TcXS>(g, x, u8, B, st);
     else if (2 * big <= g.nsm) launch_irbtc2<CS>(g, x, u8, B, st);
     else launch_irbtc2<CB>(g, x, u8, B, st);
 }
@@ -996,7 +1013,7 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes3b>("res3_5", 16), 8, 8);
     chain(make_irb<CfgRes3b>("res3_6", 16), 8, 8);
 #endif
-    chain(make_irb<CfgDown3>("conv4_1", 24), 8, 16);
+    { Group g = make_irb<CfgDown3>("conv4_1", 24); g.launch = &launch_irb_auto<CfgDown3, CfgDown3N>; chain(g, 8, 16); }
 #if YF_USE_TC
     { Group g = make_irbtc<CfgRes4Tc>("res4_1", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
     { Group g = make_irbtc<CfgRes4Tc>("res4_2", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
@@ -1010,6 +1027,7 @@ static void build_plan(yf_ctx* ctx) {
 #endif
     {
         Group g = make_irb<CfgDown4>("conv5_1", 48);
+        g.launch = &launch_irb_auto<CfgDown4, CfgDown4N>;
         g.a.skip = ctx->d_skip;
         chain(g, 16, 32);
     }
@@ -1025,12 +1043,13 @@ static void build_plan(yf_ctx* ctx) {
     { Group g{}; g.name = "conv5_2"; g.launch = &launch_pw52; g.out_ch = 96; chain(g, 32, 32); }
     const float* conv5_2 = prev;
 #if YF_USE_TC
-    chain(make_dwpwtc<CfgNeckS1Tc>("conv5_4", 128), 32, 32);
+    { Group g = make_dwpwtc<CfgNeckS1Tc>("conv5_4", 128); g.launch = &launch_dwpwtc_auto<CfgNeckS1Tc, CfgNeckS1Tc, CfgNeckS1TcN>; chain(g, 32, 32); }
 #else
     chain(make_irb<CfgNeckS1>("conv5_4", 128), 32, 32);
 #endif
     {
         Group g = heads_on_tc(ctx->nout) ? make_dwpwtc<CfgNeckS2Tc>("head_5", 0) : make_irb<CfgNeckS2>("head_5", 0);   // y = caller's head_small, set per call
+        if (heads_on_tc(ctx->nout)) g.launch = &launch_dwpwtc_auto<CfgNeckS2Tc, CfgNeckS2Tc, CfgNeckS2TcN>;
         hw(g, 32, 32); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
     {
@@ -1040,13 +1059,13 @@ static void build_plan(yf_ctx* ctx) {
         hw(g, 16, 16); g.a.x = ctx->d_skip; g.a.x2 = conv5_2; g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
 #if YF_USE_TC
-    { Group g = make_dwpwtc<CfgNeckL1Tc>("conv4_1_3", 96); g.launch = &launch_dwpwtc_auto<CfgNeckL1Tc, CfgNeckL1TcS>; chain(g, 16, 16); }
+    { Group g = make_dwpwtc<CfgNeckL1Tc>("conv4_1_3", 96); g.launch = &launch_dwpwtc_auto<CfgNeckL1Tc, CfgNeckL1TcS, CfgNeckL1TcN>; chain(g, 16, 16); }
 #else
     chain(make_irb<CfgNeckL1>("conv4_1_3", 96), 16, 16);
 #endif
     {
         Group g = heads_on_tc(ctx->nout) ? make_dwpwtc<CfgNeckL2Tc>("head_4", 0) : make_irb<CfgNeckL2>("head_4", 0);   // y = caller's head_large
-        if (heads_on_tc(ctx->nout)) g.launch = &launch_dwpwtc_auto<CfgNeckL2Tc, CfgNeckL2TcS>;
+        if (heads_on_tc(ctx->nout)) g.launch = &launch_dwpwtc_auto<CfgNeckL2Tc, CfgNeckL2TcS, CfgNeckL2TcN>;
         hw(g, 16, 16); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
 }
@@ -1098,7 +1117,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         init_thin<CfgRes1Thin>(),
 #endif
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
