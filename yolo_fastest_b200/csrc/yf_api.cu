@@ -366,7 +366,9 @@ void launch_irb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
 template <class CB, class CN>
 void launch_irb_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {      // CN: the narrow-map tile shape
     static_assert(CB::CB == CN::CB && CB::OFF_B2 == CN::OFF_B2 && CB::MC == CN::MC, "both tile shapes read the same packed weights");
-    if (g.Wout <= CN::G::TW) launch_irb<CN>(g, x, u8, B, st); else launch_irb<CB>(g, x, u8, B, st);
+    const int big = B * cdiv(g.Wout, CB::G::TW) * cdiv(g.Hout, CB::G::TH);
+    if (g.Wout <= CN::G::TW || 2 * big <= g.nsm) launch_irb<CN>(g, x, u8, B, st);      // narrow map, or a small batch: more, smaller tiles
+    else launch_irb<CB>(g, x, u8, B, st);
 }
 template <class K>
 int occ_of(K kernel, int nt, int smem) {
