@@ -1,3 +1,5 @@
+"""Distance of every tapped activation and of the heads from the float64 network, GPU path vs the reference's own fp32 arithmetic
+(GPU box): the shipped 256x320 model and its 3-channel variant on random-pixel inputs. Quoted in DESIGN.md 5.2."""
 import sys, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import yolo_fastest_b200 as yf
