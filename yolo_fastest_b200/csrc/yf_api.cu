@@ -347,8 +347,12 @@ using CfgNeckL1TcN = DwPwTcCfg<96, 96, 5, 8, 20, 16, 4, 10, false>;
 using CfgNeckL2TcN = DwPwTcCfg<96, 32, 5, 8, 20, 16, 4, 10, false, true>;
 using CfgDown3N = IrbCfg<16, 96, 24, 3, 2, 4, 20, 16, 8, 8, 4, 256, 2, true, false, false, false>;
 using CfgDown4N = IrbCfg<24, 136, 48, 3, 2, 2, 12, 16, 8, 8, 2, 128, 4, true, false, true, true>;
-using CfgNeckL1TcS = DwPwTcCfg<96, 96, 5, 4, 40, 16, 4, 10, false>;
-using CfgNeckL2TcS = DwPwTcCfg<96, 32, 5, 4, 40, 16, 4, 10, false, true>;
+using CfgNeckL1TcS = DwPwTcCfg<96, 96, 5, 4, 20, 16, 4, 10, false>;
+using CfgNeckL2TcS = DwPwTcCfg<96, 32, 5, 4, 20, 16, 4, 10, false, true>;
+using CfgNeckS1TcS = DwPwTcCfg<96, 128, 5, 4, 20, 16, 4, 10, false>;
+using CfgNeckS2TcS = DwPwTcCfg<128, 32, 5, 4, 20, 16, 4, 10, false, true>;
+using CfgRes3bTcXS = IrbTcCfg<16, 96, 16, 2, 40, 32, 2, 10, true, YF_TC3_E1ALL>;
+using CfgRes4TcXS = IrbTcCfg<24, 136, 24, 2, 20, 32, 2, 10, true, true>;
 // the tensor-core upsample+concat kernel moves the skip tensor with 128-bit loads: it needs the 1/16-resolution map to be a
 // multiple of 4 wide and even in height (true for the shipped 512x640 / 256x320 models; 416x416 falls back to upcat_kernel)
 static bool upcat_on_tc(int H, int W) { return YF_USE_TC && ((W / 16) % 4 == 0) && ((H / 16) % 2 == 0); }
@@ -450,11 +454,14 @@ void launch_irbtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st)
     const int grid = total < g.resident ? total : g.resident;
     irbtc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
 }
-template <class CB, class CS>
+template <class CB, class CS, class CXS>
 void launch_irbtc_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
-    static_assert(CB::WFLOATS == CS::WFLOATS && CB::CB == CS::CB && CB::OFF_B2 == CS::OFF_B2, "both tile shapes read the same packed weights");
+    static_assert(CB::WFLOATS == CS::WFLOATS && CB::CB == CS::CB && CB::OFF_B2 == CS::OFF_B2 && CB::WFLOATS == CXS::WFLOATS && CB::CB == CXS::CB,
+                  "all tile shapes read the same packed weights");
     const int big = B * cdiv(g.Wout, CB::G::TW) * cdiv(g.Hout, CB::G::TH);
-    if (2 * big <= g.nsm) launch_irbtc<CS>(g, x, u8, B, st); else launch_irbtc<CB>(g, x, u8, B, st);
+    if (4 * big <= g.nsm) launch_irbtc<CXS>(g, x, u8, B, st);
+    else if (2 * big <= g.nsm) launch_irbtc<CS>(g, x, u8, B, st);
+    else launch_irbtc<CB>(g, x, u8, B, st);
 }
 template <class C> int occ_irbtc() { return occ_of(irbtc_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
@@ -1005,10 +1012,10 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes3a>("res3_2", 8), 8, 8);
     chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
 #if YF_USE_TC
-    { Group g = make_irbtc<CfgRes3bTc>("res3_3", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS>; chain(g, 8, 8); }
-    { Group g = make_irbtc<CfgRes3bTc>("res3_4", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS>; chain(g, 8, 8); }
-    { Group g = make_irbtc<CfgRes3bTc>("res3_5", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS>; chain(g, 8, 8); }
-    { Group g = make_irbtc<CfgRes3bTc>("res3_6", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS>; chain(g, 8, 8); }
+    { Group g = make_irbtc<CfgRes3bTc>("res3_3", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
+    { Group g = make_irbtc<CfgRes3bTc>("res3_4", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
+    { Group g = make_irbtc<CfgRes3bTc>("res3_5", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
+    { Group g = make_irbtc<CfgRes3bTc>("res3_6", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
 #else
     chain(make_irb<CfgRes3b>("res3_3", 16), 8, 8);
     chain(make_irb<CfgRes3b>("res3_4", 16), 8, 8);
@@ -1017,10 +1024,10 @@ static void build_plan(yf_ctx* ctx) {
 #endif
     { Group g = make_irb<CfgDown3>("conv4_1", 24); g.launch = &launch_irb_auto<CfgDown3, CfgDown3N>; chain(g, 8, 16); }
 #if YF_USE_TC
-    { Group g = make_irbtc<CfgRes4Tc>("res4_1", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
-    { Group g = make_irbtc<CfgRes4Tc>("res4_2", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
-    { Group g = make_irbtc<CfgRes4Tc>("res4_3", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
-    { Group g = make_irbtc<CfgRes4Tc>("res4_4", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS>; chain(g, 16, 16); }
+    { Group g = make_irbtc<CfgRes4Tc>("res4_1", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>; chain(g, 16, 16); }
+    { Group g = make_irbtc<CfgRes4Tc>("res4_2", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>; chain(g, 16, 16); }
+    { Group g = make_irbtc<CfgRes4Tc>("res4_3", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>; chain(g, 16, 16); }
+    { Group g = make_irbtc<CfgRes4Tc>("res4_4", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>; chain(g, 16, 16); }
 #else
     chain(make_irb<CfgRes4>("res4_1", 24), 16, 16);
     chain(make_irb<CfgRes4>("res4_2", 24), 16, 16);
@@ -1045,13 +1052,13 @@ static void build_plan(yf_ctx* ctx) {
     { Group g{}; g.name = "conv5_2"; g.launch = &launch_pw52; g.out_ch = 96; chain(g, 32, 32); }
     const float* conv5_2 = prev;
 #if YF_USE_TC
-    { Group g = make_dwpwtc<CfgNeckS1Tc>("conv5_4", 128); g.launch = &launch_dwpwtc_auto<CfgNeckS1Tc, CfgNeckS1Tc, CfgNeckS1TcN>; chain(g, 32, 32); }
+    { Group g = make_dwpwtc<CfgNeckS1Tc>("conv5_4", 128); g.launch = &launch_dwpwtc_auto<CfgNeckS1Tc, CfgNeckS1TcS, CfgNeckS1TcN>; chain(g, 32, 32); }
 #else
     chain(make_irb<CfgNeckS1>("conv5_4", 128), 32, 32);
 #endif
     {
         Group g = heads_on_tc(ctx->nout) ? make_dwpwtc<CfgNeckS2Tc>("head_5", 0) : make_irb<CfgNeckS2>("head_5", 0);   // y = caller's head_small, set per call
-        if (heads_on_tc(ctx->nout)) g.launch = &launch_dwpwtc_auto<CfgNeckS2Tc, CfgNeckS2Tc, CfgNeckS2TcN>;
+        if (heads_on_tc(ctx->nout)) g.launch = &launch_dwpwtc_auto<CfgNeckS2Tc, CfgNeckS2TcS, CfgNeckS2TcN>;
         hw(g, 32, 32); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
     {
@@ -1119,7 +1126,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         init_thin<CfgRes1Thin>(),
 #endif
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
