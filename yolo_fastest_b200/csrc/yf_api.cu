@@ -2,6 +2,7 @@
 // the launch plan of fused groups, and the entry points. Kernels live in yf_kernels.cuh / yf_post.cuh.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -15,7 +16,7 @@
 #include "yf_kernels.cuh"
 #include "yf_post.cuh"
 #include "yf_tc.cuh"
-#include "yf_thin.cuh"
+#include "yf_wirb.cuh"
 #include "yf_tcpw.cuh"
 #include "yf_tcup.cuh"
 #include "yf_tcirb2.cuh"
@@ -103,7 +104,16 @@ void set_err(std::string* dst, const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
+// tensor map of a group's input (warp-streaming kernels): re-encoded only when the input pointer or the batch changes
+struct TmaCache {
+    CUtensorMap map;
+    const void* ptr = nullptr;
+    int B = 0;
+    bool failed = false;
+};
+
 struct GroupArgs {
+    TmaCache* tc = nullptr;      // the owning group's tensor-map cache
     int nsm = 148;               // SM count
     int resident = 148;          // persistent grid = CTAs that are co-resident on the device for this group's kernel
     const float* x = nullptr;    // input activation
@@ -122,6 +132,7 @@ struct Group {
     GroupArgs a;
     int out_ch;                                         // channels of y (0 for heads: written to caller memory)
     int64_t w_off;                                      // offset into dev blob (floats)
+    TmaCache tcache;
 };
 
 struct yf_ctx {
@@ -201,14 +212,22 @@ using CfgStem3 = StemCfg<8, 40, 256, 2, 3>;          // 3-channel (colour) input
 #define YF_CFGRES1 IrbCfg<4, 8, 4, 3, 1, 8, 80, 8, 8, 4, 8, 256, 3, true, true, false, false>
 #endif
 using CfgRes1 = YF_CFGRES1;
-// register-resident kernel for the thin block res1_1: ThinCfg<CIN, CMID, COUT, TH, TW, RH, MPAR, min blocks/SM, RES>
-#ifndef YF_CFGRES1_THIN
-#define YF_CFGRES1_THIN ThinCfg<4, 8, 4, 32, 64, 4, 1, 2, true>
+// warp-streaming engine (yf_wirb.cuh) for the thin groups: WirbCfg<CIN, CMID, COUT, S, SPX, NSL, RC, warps, RES, W2 in registers>
+#ifndef YF_USE_WIRB
+#define YF_USE_WIRB 1    // 0: the thin groups stay on the block-cooperative FFMA engine (comparison arm)
 #endif
-using CfgRes1Thin = YF_CFGRES1_THIN;
-#ifndef YF_USE_THIN
-#define YF_USE_THIN 0   // measured (B200, 640x512, batch 256): 0.44 ms = no better than the generic engine's 0.45 ms; the kernel is
-#endif                  // register-bound (255 registers, 8 warps/SM) — kept as an opt-in experiment, see DESIGN.md
+#ifndef YF_CFGRES1_W
+#define YF_CFGRES1_W WirbCfg<4, 8, 4, 1, 4, 8, 6, 16, true, true>
+#endif
+using CfgRes1W = YF_CFGRES1_W;
+#ifndef YF_CFGRES2_W
+#define YF_CFGRES2_W WirbCfg<8, 32, 8, 1, 8, 2, 6, 12, true, false>
+#endif
+using CfgRes2W = YF_CFGRES2_W;
+#ifndef YF_CFGDOWN2_W
+#define YF_CFGDOWN2_W WirbCfg<8, 32, 8, 2, 4, 2, 8, 12, false, false>
+#endif
+using CfgDown2W = YF_CFGDOWN2_W;
 
 #ifndef YF_CFGDENSE
 #define YF_CFGDENSE DenseCfg<8, 40, 4, 128, 3, 2>
@@ -394,16 +413,39 @@ void launch_upcat_tc(const GroupArgs& g, const void*, bool, int B, cudaStream_t 
     upcat_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.x2, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
 }
 
+// warp-streaming groups: one warp per (image, band of R output rows, strip of OW columns). The band height is chosen per launch:
+// it trades the 2 halo rows per band against the load balance of units over the resident warps.
 template <class C>
-void launch_thin(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
-    const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
-    const int total = B * tx * ty;
-    const int grid = total < g.resident ? total : g.resident;
-    thin_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+int wirb_band_rows(int B, int Hout, int Wout, int warps) {
+    const int nstrips = cdiv(Wout, C::OW);
+    long long best_cost = -1;
+    int best_R = 1;
+    for (int nch = 1; nch <= 16; ++nch) {
+        const int R = C::S == 1 ? nch * C::RC - 2 : (nch * C::RC - 1) / 2;      // the tallest band whose input rows fill nch boxes
+        if (R < 1) continue;
+        const long long units = (long long)B * nstrips * cdiv(Hout, R);
+        const long long cost = ((units + warps - 1) / warps) * (nch * C::RC + 2);  // box rows per warp (+ per-unit set-up)
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_R = R; }
+        if (R >= Hout) break;
+    }
+    return best_R;
 }
-template <class C> int occ_thin() { return occ_of(thin_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
-cudaError_t init_thin() { return cudaFuncSetAttribute(thin_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
+void launch_wirb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    TmaCache* tc = g.tc;
+    if (tc->ptr != g.x || tc->B != B) {
+        tc->failed = tma_make_map4(&tc->map, g.x, 4, B, C::CIN, g.Hin, g.Win, C::XW, C::RC, C::CIN) != 0;
+        tc->ptr = g.x; tc->B = B;
+    }
+    if (tc->failed) return;
+    const int R = wirb_band_rows<C>(B, g.Hout, g.Wout, g.nsm * C::NW);
+    const int nstrips = cdiv(g.Wout, C::OW), nbands = cdiv(g.Hout, R);
+    const int total = B * nstrips * nbands;
+    const int grid = std::min(g.nsm, cdiv(total, C::NW));
+    wirb_kernel<C><<<grid, C::NW * 32, C::SMEM_BYTES, st>>>(tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
+}
+template <class C>
+cudaError_t init_wirb() { return cudaFuncSetAttribute(wirb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
 
 template <class C>
 void launch_dwpwtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
@@ -579,19 +621,19 @@ inline void put_kmajor_split(float* hi, float* lo, int n, int k, int K, float w)
     lo[idx] = tf32_rna_host(w - h);      // rounded, not left to the tensor core's truncation (which would bias every product the same way)
 }
 
+// warp-streaming group: [W1: CIN x CMID][b1][Wd: 9 x CMID][bd][W2: COUT x CMID][b2]
 template <class C>
-int64_t pack_thin(std::vector<float>& out, const Folded& f, const std::string& n1, const std::string& nd, const std::string& n2) {
+int64_t pack_wirb(std::vector<float>& out, const Folded& f, const std::string& n1, const std::string& nd, const std::string& n2) {
     pad4(out);
     const int64_t off = (int64_t)out.size();
     out.resize(off + C::WFLOATS, 0.f);
     float* o = out.data() + off;
     for (int m = 0; m < C::CMID; ++m) {
-        float* wm = o + (int64_t)m * C::WM;
-        for (int k = 0; k < C::CIN; ++k) wm[C::OFF_W1 + k] = f.w(n1)[m * C::CIN + k];
-        wm[C::OFF_B1] = f.b(n1)[m];
-        for (int t = 0; t < 9; ++t) wm[C::OFF_WD + t] = f.w(nd)[m * 9 + t];
-        wm[C::OFF_BD] = f.b(nd)[m];
-        for (int n = 0; n < C::COUT; ++n) wm[C::OFF_W2 + n] = f.w(n2)[n * C::CMID + m];
+        for (int k = 0; k < C::CIN; ++k) o[C::OFF_W1 + k * C::CMID + m] = f.w(n1)[m * C::CIN + k];
+        o[C::OFF_B1 + m] = f.b(n1)[m];
+        for (int t = 0; t < 9; ++t) o[C::OFF_WD + t * C::CMID + m] = f.w(nd)[m * 9 + t];
+        o[C::OFF_BD + m] = f.b(nd)[m];
+        for (int n = 0; n < C::COUT; ++n) o[C::OFF_W2 + n * C::CMID + m] = f.w(n2)[n * C::CMID + m];
     }
     for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
     return off;
@@ -855,11 +897,10 @@ int64_t pack_upcat(std::vector<float>& out, const Folded& f) {
 }
 
 template <class C>
-Group make_thin(const char* name, int out_ch) {
+Group make_wirb(const char* name, int out_ch) {
     Group g{};
     g.name = name;
-    g.launch = &launch_thin<C>;
-    g.occupancy = &occ_thin<C>;
+    g.launch = &launch_wirb<C>;
     g.out_ch = out_ch;
     return g;
 }
@@ -995,8 +1036,8 @@ static void build_plan(yf_ctx* ctx) {
         g.a.Hin = H; g.a.Win = W; g.a.Hout = H / 2; g.a.Wout = W / 2;
         g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
     }
-#if YF_USE_THIN
-    chain(make_thin<CfgRes1Thin>("res1_1", 4), 2, 2);
+#if YF_USE_WIRB
+    chain(make_wirb<CfgRes1W>("res1_1", 4), 2, 2);
 #else
     chain(make_irb<CfgRes1>("res1_1", 4), 2, 2);
 #endif
@@ -1005,9 +1046,15 @@ static void build_plan(yf_ctx* ctx) {
 #else
     { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense; g.occupancy = &occ_dense; g.out_ch = 8; chain(g, 2, 4); }
 #endif
+#if YF_USE_WIRB
+    chain(make_wirb<CfgRes2W>("res2_1", 8), 4, 4);
+    chain(make_wirb<CfgRes2W>("res2_2", 8), 4, 4);
+    chain(make_wirb<CfgDown2W>("conv3_1", 8), 4, 8);
+#else
     chain(make_irb<CfgRes2>("res2_1", 8), 4, 4);
     chain(make_irb<CfgRes2>("res2_2", 8), 4, 4);
     chain(make_irb<CfgDown2>("conv3_1", 8), 4, 8);
+#endif
     chain(make_irb<CfgRes3a>("res3_1", 8), 8, 8);
     chain(make_irb<CfgRes3a>("res3_2", 8), 8, 8);
     chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
@@ -1085,6 +1132,7 @@ static void set_sm_count(yf_ctx* ctx) {
     for (Group& g : ctx->groups) {
         g.a.nsm = nsm;
         g.a.resident = nsm * (g.occupancy ? g.occupancy() : 1);
+        g.a.tc = &g.tcache;              // the plan is complete: group addresses are stable from here on
     }
 }
 
@@ -1122,9 +1170,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_tc_kernel<CfgUpCatTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCatTc::SMEM_BYTES),
         init_irb<CfgRes1>(),
-#if YF_USE_THIN
-        init_thin<CfgRes1Thin>(),
-#endif
+        init_wirb<CfgRes1W>(), init_wirb<CfgRes2W>(), init_wirb<CfgDown2W>(),
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
         init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
@@ -1180,14 +1226,20 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
         offs.push_back(pack_irb<C>(P, f, n + ".conv1", n + ".conv2", n + ".conv3", "", 0));
     };
     offs.push_back(ctx->in_ch == 3 ? pack_stem<CfgStem3>(P, f) : pack_stem<CfgStem>(P, f));
-#if YF_USE_THIN
-    offs.push_back(pack_thin<CfgRes1Thin>(P, f, "res1_1.conv1", "res1_1.conv2", "res1_1.conv3"));
+#if YF_USE_WIRB
+    offs.push_back(pack_wirb<CfgRes1W>(P, f, "res1_1.conv1", "res1_1.conv2", "res1_1.conv3"));
 #else
     res(CfgRes1{}, "res1_1");
 #endif
     offs.push_back(YF_DENSE_TC ? pack_dense_tc(P, f) : pack_dense(P, f));
+#if YF_USE_WIRB
+    offs.push_back(pack_wirb<CfgRes2W>(P, f, "res2_1.conv1", "res2_1.conv2", "res2_1.conv3"));
+    offs.push_back(pack_wirb<CfgRes2W>(P, f, "res2_2.conv1", "res2_2.conv2", "res2_2.conv3"));
+    offs.push_back(pack_wirb<CfgDown2W>(P, f, "conv2_2", "conv2_3", "conv3_1"));
+#else
     res(CfgRes2{}, "res2_1"); res(CfgRes2{}, "res2_2");
     offs.push_back(pack_irb<CfgDown2>(P, f, "conv2_2", "conv2_3", "conv3_1", "", 0));
+#endif
     res(CfgRes3a{}, "res3_1"); res(CfgRes3a{}, "res3_2");
     offs.push_back(pack_irb<CfgWide3>(P, f, "conv3_2", "conv3_3", "conv3_4", "", 0));
 #if YF_USE_TC
@@ -1282,6 +1334,8 @@ static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* hea
     }
     if (fork) CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU(cudaGetLastError());
+    for (Group& g : ctx->groups)
+        if (g.tcache.failed) { set_err(&ctx->err, "cuTensorMapEncodeTiled failed for group '%s'", g.name); g.tcache.ptr = nullptr; return YF_ERR_CUDA; }
     return YF_OK;
 }
 
