@@ -109,6 +109,7 @@ struct TmaCache {
     CUtensorMap map;
     const void* ptr = nullptr;
     int B = 0;
+    bool u8 = false;
     bool failed = false;
 };
 
@@ -217,7 +218,7 @@ using CfgRes1 = YF_CFGRES1;
 #define YF_USE_WIRB 1    // 0: the thin groups stay on the block-cooperative FFMA engine (comparison arm)
 #endif
 #ifndef YF_CFGRES1_W
-#define YF_CFGRES1_W WirbCfg<4, 8, 4, 1, 4, 8, 6, 16, true, true>
+#define YF_CFGRES1_W WirbCfg<4, 8, 4, 1, 4, 8, 6, 12, true, true>
 #endif
 using CfgRes1W = YF_CFGRES1_W;
 #ifndef YF_CFGRES2_W
@@ -228,6 +229,10 @@ using CfgRes2W = YF_CFGRES2_W;
 #define YF_CFGDOWN2_W WirbCfg<8, 32, 8, 2, 4, 2, 8, 12, false, false>
 #endif
 using CfgDown2W = YF_CFGDOWN2_W;
+#ifndef YF_CFGSTEM_W
+#define YF_CFGSTEM_W WstemCfg<12>
+#endif
+using CfgStemW = YF_CFGSTEM_W;
 
 #ifndef YF_CFGDENSE
 #define YF_CFGDENSE DenseCfg<8, 40, 4, 128, 3, 2>
@@ -437,6 +442,7 @@ void launch_wirb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) 
         tc->failed = tma_make_map4(&tc->map, g.x, 4, B, C::CIN, g.Hin, g.Win, C::XW, C::RC, C::CIN) != 0;
         tc->ptr = g.x; tc->B = B;
     }
+    if (g.Wout % C::SPX) tc->failed = true;               // the edge masks assume whole strips (true for every H, W multiple of 32)
     if (tc->failed) return;
     const int R = wirb_band_rows<C>(B, g.Hout, g.Wout, g.nsm * C::NW);
     const int nstrips = cdiv(g.Wout, C::OW), nbands = cdiv(g.Hout, R);
@@ -444,6 +450,31 @@ void launch_wirb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) 
     const int grid = std::min(g.nsm, cdiv(total, C::NW));
     wirb_kernel<C><<<grid, C::NW * 32, C::SMEM_BYTES, st>>>(tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
 }
+// stem group on the warp-streaming engine (single-channel input): the raw image is the TMA tensor, fp32 or uint8
+template <class C>
+void launch_wstem(const GroupArgs& g, const void* xin, bool u8in, int B, cudaStream_t st) {
+    TmaCache* tc = g.tc;
+    if (tc->ptr != xin || tc->B != B || tc->u8 != u8in) {
+        tc->failed = (u8in ? tma_make_map4(&tc->map, xin, 1, B, 1, g.Hin, g.Win, C::RAWWU, C::RAWH, 1)
+                           : tma_make_map4(&tc->map, xin, 4, B, 1, g.Hin, g.Win, C::RAWW, C::RAWH, 1)) != 0;
+        tc->ptr = xin; tc->B = B; tc->u8 = u8in;
+    }
+    if (g.Wout % C::SPX) tc->failed = true;
+    if (tc->failed) return;
+    const int R = wirb_band_rows<C>(B, g.Hout, g.Wout, g.nsm * C::NW);
+    const int nstrips = cdiv(g.Wout, C::OW), nbands = cdiv(g.Hout, R);
+    const int total = B * nstrips * nbands;
+    const int grid = std::min(g.nsm, cdiv(total, C::NW));
+    if (u8in) wstem_kernel<C, true><<<grid, C::NW * 32, C::template smem_bytes<true>(), st>>>(tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
+    else wstem_kernel<C, false><<<grid, C::NW * 32, C::template smem_bytes<false>(), st>>>(tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
+}
+template <class C>
+cudaError_t init_wstem() {
+    cudaError_t e = cudaFuncSetAttribute(wstem_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::template smem_bytes<true>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(wstem_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::template smem_bytes<false>());
+}
+
 template <class C>
 cudaError_t init_wirb() { return cudaFuncSetAttribute(wirb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
 
@@ -789,6 +820,26 @@ int64_t pack_irbtc(std::vector<float>& out, const Folded& f, const std::string& 
     return off;
 }
 
+// stem on the warp-streaming engine: [W0: 9 x 8][b0][W1: 8 x 8 (k-major)][b1][Wd: 9 x 8][bd][W2: 4 x 8 (n-major)][b2]
+template <class C>
+int64_t pack_wstem(std::vector<float>& out, const Folded& f) {
+    pad4(out);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int c = 0; c < 8; ++c) {
+        for (int t = 0; t < 9; ++t) o[C::OFF_W0 + t * 8 + c] = f.w("conv0")[c * 9 + t];
+        o[C::OFF_B0 + c] = f.b("conv0")[c];
+        for (int k = 0; k < 8; ++k) o[C::OFF_W1 + k * 8 + c] = f.w("conv1_2")[c * 8 + k];
+        o[C::OFF_B1 + c] = f.b("conv1_2")[c];
+        for (int t = 0; t < 9; ++t) o[C::OFF_WD + t * 8 + c] = f.w("conv1_3")[c * 9 + t];
+        o[C::OFF_BD + c] = f.b("conv1_3")[c];
+        for (int n = 0; n < 4; ++n) o[C::OFF_W2 + n * 8 + c] = f.w("conv1_4")[n * 8 + c];
+    }
+    for (int n = 0; n < 4; ++n) o[C::OFF_B2 + n] = f.b("conv1_4")[n];
+    return off;
+}
+
 template <class C>
 int64_t pack_stem(std::vector<float>& out, const Folded& f) {
     pad4(out);
@@ -1032,6 +1083,7 @@ static void build_plan(yf_ctx* ctx) {
     {
         Group g{}; g.name = "conv1_4"; g.out_ch = 4;
         if (ctx->in_ch == 3) { g.launch = &launch_stem<CfgStem3>; g.occupancy = &occ_stem3; }
+        else if (YF_USE_WIRB) { g.launch = &launch_wstem<CfgStemW>; }
         else { g.launch = &launch_stem<CfgStem>; g.occupancy = &occ_stem; }
         g.a.Hin = H; g.a.Win = W; g.a.Hout = H / 2; g.a.Wout = W / 2;
         g.a.y = ctx->d_act[ai++]; prev = g.a.y; G.push_back(g);
@@ -1170,7 +1222,7 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_tc_kernel<CfgUpCatTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCatTc::SMEM_BYTES),
         init_irb<CfgRes1>(),
-        init_wirb<CfgRes1W>(), init_wirb<CfgRes2W>(), init_wirb<CfgDown2W>(),
+        init_wirb<CfgRes1W>(), init_wirb<CfgRes2W>(), init_wirb<CfgDown2W>(), init_wstem<CfgStemW>(),
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
         init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
@@ -1225,7 +1277,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
         using C = decltype(tag);
         offs.push_back(pack_irb<C>(P, f, n + ".conv1", n + ".conv2", n + ".conv3", "", 0));
     };
-    offs.push_back(ctx->in_ch == 3 ? pack_stem<CfgStem3>(P, f) : pack_stem<CfgStem>(P, f));
+    offs.push_back(ctx->in_ch == 3 ? pack_stem<CfgStem3>(P, f) : YF_USE_WIRB ? pack_wstem<CfgStemW>(P, f) : pack_stem<CfgStem>(P, f));
 #if YF_USE_WIRB
     offs.push_back(pack_wirb<CfgRes1W>(P, f, "res1_1.conv1", "res1_1.conv2", "res1_1.conv3"));
 #else
