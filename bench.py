@@ -134,9 +134,18 @@ def synthetic_u8(B, H, W, seed):
     return torch.randint(0, 256, (B, H, W), generator=g, dtype=torch.uint8)
 
 
-def cpu_reference_pass(sd, io, u8):
-    """The reference's CPU path restated by the oracle: PyTorch CPU forward + Python decode/sort/NMS loops per image
-    (detect.py:46 reads batch element 0 only, so B > 1 loops decode per image as BASELINE.md §3 prescribes)."""
+def cpu_reference_pass(sd, io, u8, res):
+    """One pass of the reference's CPU path over a batch: (forward s, post-process s, detections, kind).
+    kind "reference": the UNMODIFIED reference staged under baseline/_ref (baseline/ref_arm.py: its own YoloFastest module and
+    YOLO_post_process object, driven as Detect_YOLO.batch_detect drives them). kind "port": the oracle's restatement — only when
+    baseline/_ref is absent (a checkout that never ran build() next to /root/reference)."""
+    from baseline import ref_arm
+    if ref_arm.available():
+        pipe = _REF.get(res)
+        if pipe is None:
+            pipe = _REF[res] = ref_arm.RefPipeline(res, sd)
+        a, b, n = pipe.run(u8)
+        return a, b, n, "reference"
     from oracle import yolo_oracle as O
     x = (u8.float().unsqueeze(1) - 128.0) / 255.0
     t0 = time.perf_counter()
@@ -147,7 +156,10 @@ def cpu_reference_pass(sd, io, u8):
         n_det += len(O.detect_postprocess(pred, io["anchors"], io["input_shape"], io["conf_thre"], io["nms_thre"],
                                           io["num_anchors"], io["num_cls"], batch_index=b))
     t2 = time.perf_counter()
-    return t1 - t0, t2 - t1, n_det
+    return t1 - t0, t2 - t1, n_det, "port"
+
+
+_REF = {}
 
 
 def run_reference(args, cfg, sd, rank, world):
@@ -160,11 +172,12 @@ def run_reference(args, cfg, sd, rank, world):
     torch.set_num_threads(cores)
     sample = args.cpu_sample
     u8 = synthetic_u8(sample, H, W, 1000)
+    kind = "port"
     for _ in range(args.warmup):
-        cpu_reference_pass(sd, io, u8)
+        cpu_reference_pass(sd, io, u8, args.res)
     fwd = post = 0.0
     for _ in range(args.steps):
-        a, b, _ = cpu_reference_pass(sd, io, u8)
+        a, b, _, kind = cpu_reference_pass(sd, io, u8, args.res)
         fwd += a; post += b
     total = fwd + post
     value = sample * args.steps / total
@@ -173,7 +186,7 @@ def run_reference(args, cfg, sd, rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%dx%d synthetic uint8 images, shipped %s checkpoint, conf %.2f nms %.2f; CPU sample of %d images per step"
                        % (W, H, args.res, io["conf_thre"], io["nms_thre"], sample)},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
                              "sample": "%d images/step x %d steps; forward %.1f ms/img, post-process %.2f ms/img; torch %s"
                              % (sample, args.steps, 1000 * fwd / (sample * args.steps), 1000 * post / (sample * args.steps), torch.__version__)},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -218,7 +231,7 @@ def main():
     __graft_entry__.build()
     import torch.distributed as dist
     from yolo_fastest_b200 import Detect_YOLO, _lib
-    from yolo_fastest_b200.dist import gather_detections
+    from yolo_fastest_b200.dist import gather_compact, shard_range, split_records
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -241,7 +254,7 @@ def main():
     def step_device():
         out, counts, status = det.detect_device(x_dev, args.max_det)
         if world > 1:
-            gather_detections(out, counts, n_total, dst=0, to_host=False)     # one NCCL gather, results stay on rank 0's device
+            gather_compact(out, counts, n_total, dst=0, ctx=det.model._ctx)   # compaction kernel + one NCCL gather on the side stream
         return counts
 
     def step_e2e():
@@ -288,15 +301,18 @@ def main():
                     det.submit_batch(u8b[(i + 1) & 1], (i + 1) & 1, max_det=args.max_det)
                 rows = det.collect(i & 1, raw=True)
             return rows
-        # N > 1: every rank runs the same double-buffered loop with its results left on the device, returns its slab to
-        # rank 0 with one NCCL gather per step, and rank 0 reads the whole job's detections back to the host
+        # N > 1: every rank runs the same double-buffered loop with its results left on the device and returns them to rank 0 with one
+        # compacted NCCL gather per step on a side stream; rank 0 reads step i's detections from pinned memory while step i + 1 runs
         pend = det.submit_batch_device(u8b[0], 0, max_det=args.max_det)
-        res = None
+        res, prev = None, None
         for i in range(nsteps):
             nxt = det.submit_batch_device(u8b[(i + 1) & 1], (i + 1) & 1, max_det=args.max_det) if i + 1 < nsteps else None
             det.wait(i & 1)
-            res = gather_detections(pend[0], pend[1], n_total, dst=0, to_host=True)
-            pend = nxt
+            h = gather_compact(pend[0], pend[1], n_total, dst=0, ctx=det.model._ctx)
+            if prev is not None:
+                res = prev.result()
+            prev, pend = h, nxt
+        res = prev.result()
         return res
 
     run_e2e(3)
@@ -317,11 +333,52 @@ def main():
         step_e2e()
     sync_ms = 1000.0 * (time.perf_counter() - t0) / max(2, args.steps // 4)
 
+    # ---- N > 1: the gathered result must be what ONE GPU computes for the whole job, outside the timed region ------
+    gather_check = None
+    if world > 1:
+        out, cnt = det.submit_batch_device(u8b[0], 0, max_det=args.max_det)
+        det.wait(0)
+        recs, cnts = gather_compact(out, cnt, n_total, dst=0, ctx=det.model._ctx).result()
+        if rank == 0:
+            want = []
+            for r in range(world):          # rank 0 regenerates every rank's shard (seeded) and runs it on its own GPU
+                nr = dist_shard(args.global_batch, r, world) if args.global_batch else args.batch
+                want += det.detect_batch(synthetic_u8(nr, H, W, 1000 + r), max_det=args.max_det, raw=True)
+            got = split_records(recs, cnts)
+            same = len(got) == len(want) and all(g_.tobytes() == w_.tobytes() for g_, w_ in zip(got, want))
+            gather_check = {"ok": bool(same), "images": len(want), "records": int(sum(len(w_) for w_ in want)),
+                            "what": "NCCL-gathered per-image lists of all ranks == rank 0's own single-GPU detect_batch of every shard, byte for byte"}
+            if not same:
+                raise SystemExit("gathered detections differ from the single-GPU result: %r" % (gather_check,))
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
+
+    # ---- batch-1 latency (BASELINE config 2) through the blocking public call: CUDA-graph replay of the 31 launches -----------------
+    latency = None
+    if world == 1 and B >= 1:
+        one = u8[:1].clone().pin_memory()
+        for _ in range(20):
+            det.detect_batch(one, max_det=args.max_det, raw=True)
+        nlat = 200
+        t0 = time.perf_counter()
+        for _ in range(nlat):
+            det.detect_batch(one, max_det=args.max_det, raw=True)
+        lat_ms = 1000.0 * (time.perf_counter() - t0) / nlat
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        x1 = x_dev[:1].contiguous()
+        for _ in range(20):
+            det.detect_device(x1, args.max_det)
+        ev[0].record()
+        for _ in range(nlat):
+            det.detect_device(x1, args.max_det)
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        latency = {"batch": 1, "ms_e2e": round(lat_ms, 4), "api": "Detect_YOLO.detect_batch -> yf_detect_host_u8 (H2D, graph replay, D2H, sync), %d calls after 20 warm-ups" % nlat,
+                   "ms_device_stream": round(ev[0].elapsed_time(ev[1]) / nlat, 4), "device_api": "yf_detect on a resident fp32 image, back to back on one stream"}
 
     # ---- per-kernel roofline (rank 0): CUDA events around every group launch of one forward ----------------------
     prof = det.model.profile(x_dev)
@@ -334,29 +391,58 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     total_ms = sum(m for _, m in prof)
+    # which engine runs a group decides the roof that binds it: the tcgen05 groups are contractions on the tensor pipe (bound
+    # "tensor"), every other group runs on the FP32 CUDA cores and moves its activations once (bound = the larger of its HBM time and
+    # its FP32 time; "hbm" for the thin 4-8 channel groups whose HBM time is the larger one)
+    TENSOR = {"conv2_1", "res3_3", "res3_4", "res3_5", "res3_6", "res4_1", "res4_2", "res4_3", "res4_4", "res5_1", "res5_2", "res5_3",
+              "res5_4", "res5_5", "conv5_4", "head_5", "conv4_1_1", "conv4_1_3", "head_4"}
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    tf32_peak = bf16_peak / 2.0                              # kind::tf32 issues at half the bf16 rate
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")))
+    except Exception:
+        pass
     kernels = []
     for name, m in prof:
         w = work[name]
         gbs = w["bytes"] * B / (m * 1e-3) / 1e9
         tfl = 2 * w["macs"] * B / (m * 1e-3) / 1e12
-        kernels.append({"name": name, "ms": round(m, 4), "share": round(m / total_ms, 4), "GB/s": round(gbs, 1), "hbm_frac": round(gbs / hbm_peak, 4),
-                        "TFLOP/s": round(tfl, 2), "fp32_frac": round(tfl / FP32_PEAK_TFLOPS, 4)})
+        t_hbm = w["bytes"] * B / (hbm_peak * 1e9) * 1e3
+        t_flop = 2 * w["macs"] * B / (FP32_PEAK_TFLOPS * 1e12) * 1e3
+        k = {"name": name, "ms": round(m, 4), "share": round(m / total_ms, 4), "GB/s": round(gbs, 1), "hbm_frac": round(gbs / hbm_peak, 4),
+             "TFLOP/s": round(tfl, 2), "fp32_frac": round(tfl / FP32_PEAK_TFLOPS, 4),
+             "bound": "tensor" if name in TENSOR else ("hbm" if t_hbm >= t_flop else "fp32"),
+             "roof_ms": round(max(t_hbm, t_flop), 4), "roof_frac": round(max(t_hbm, t_flop) / m, 4)}
+        if name in TENSOR:
+            k["tf32_frac_executed"] = round(3 * tfl / tf32_peak, 4)       # 3xTF32: three tensor-core products per fp32 product
+        if name in ncu.get("kernels", {}):
+            k["ncu"] = ncu["kernels"][name]
+        kernels.append(k)
     top = max(kernels, key=lambda k: k["ms"])
-    # DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu pass
-    # of this same workload (tools/launch_report.py -> profiles/r01_traffic.json); null when no capture matches the workload
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tr.get("workload") == "%dx%d b%d" % (W, H, B):
-            traffic = tr["bytes_per_launch"].get(top["name"])
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": top["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": traffic,
-                "kernel": top["name"], "share_of_forward": top["share"], "peak_source": peak_src,
-                "note": "fused groups are FP32 CUDA-core bound (48 FLOP/B overall); see fp32"}
+    # DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) and its tensor-pipe utilisation come
+    # from the committed ncu pass of this same workload (profiles/r02_ncu_metrics.json, written by tools/ncu_metrics.py from a
+    # `ncu --set full` capture at batch 256) — a profiler cannot run inside the timed process; null when no capture matches
+    traffic, traffic_source = None, None
+    if ncu.get("workload") == "%dx%d b%d" % (W, H, B) and top["name"] in ncu.get("kernels", {}):
+        traffic = ncu["kernels"][top["name"]].get("dram_bytes")
+        traffic_source = "profiles/r02_ncu_metrics.json (%s)" % ncu.get("source", "ncu --set full")
+    if top["bound"] == "tensor":
+        roofline = {"bound": "tensor", "achieved": top["TFLOP/s"], "peak": bf16_peak, "unit": "TFLOP/s", "frac": round(top["TFLOP/s"] / bf16_peak, 4),
+                    "traffic": traffic, "traffic_source": traffic_source, "kernel": top["name"], "share_of_forward": top["share"],
+                    "peak_source": "measured dense bf16 (MEASURED_PEAKS.json bf16_tflops_sustained)" if "bf16_tflops_sustained" in peaks else "fallback 1.59 PFLOP/s",
+                    "tf32_peak": tf32_peak, "executed_TFLOP/s": round(3 * top["TFLOP/s"], 1), "frac_of_tf32_executed": top.get("tf32_frac_executed"),
+                    "tensor_pipe_util_ncu": top.get("ncu", {}).get("tensor_pipe_pct"),
+                    "hbm_GB/s": top["GB/s"], "hbm_frac": top["hbm_frac"],
+                    "note": "fp32 parity needs 3xTF32 (hi*hi + hi*lo + lo*hi): algorithmic FLOPs are a third of the executed tensor FLOPs; the kernel is bound by its CUDA-core producer warps, not by the pipe"}
+    else:
+        roofline = {"bound": top["bound"], "achieved": top["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": traffic,
+                    "traffic_source": traffic_source, "kernel": top["name"], "share_of_forward": top["share"], "peak_source": peak_src}
     fp32 = {"kernel": top["name"], "achieved": top["TFLOP/s"], "peak": round(FP32_PEAK_TFLOPS, 1), "unit": "TFLOP/s", "frac": top["fp32_frac"],
             "whole_forward_TFLOP/s": round(2 * sum(g["macs"] for g in work.values()) * B / (total_ms * 1e-3) / 1e12, 2),
-            "whole_forward_GB/s": round(sum(g["bytes"] for g in work.values()) * B / (total_ms * 1e-3) / 1e9, 1)}
+            "whole_forward_GB/s": round(sum(g["bytes"] for g in work.values()) * B / (total_ms * 1e-3) / 1e9, 1),
+            "whole_forward_roof_ms": round(sum(k["roof_ms"] for k in kernels), 4),
+            "whole_forward_roof_frac": round(sum(k["roof_ms"] for k in kernels) / total_ms, 4)}
 
     # ---- pre-processing kernel: 512x640 BGR frames -> network input, CUDA events, HBM-bound ---------------
     preprocess = None
@@ -387,13 +473,14 @@ def main():
         torch.set_num_threads(cores)
         sample = args.cpu_sample
         cu8 = synthetic_u8(sample, H, W, 1000)
-        cpu_reference_pass(sd, io, cu8)
+        cpu_reference_pass(sd, io, cu8, args.res)
         fwd = post = 0.0
         reps = 2
+        kind = "port"
         for _ in range(reps):
-            a, b, _ = cpu_reference_pass(sd, io, cu8)
+            a, b, _, kind = cpu_reference_pass(sd, io, cu8, args.res)
             fwd += a; post += b
-        cpu_baseline = {"value": sample * reps / (fwd + post), "unit": "images/s", "cores": cores, "kind": "port",
+        cpu_baseline = {"value": sample * reps / (fwd + post), "unit": "images/s", "cores": cores, "kind": kind,
                         "sample": "%d images x %d passes after 1 warm-up; forward %.1f ms/img, post-process %.2f ms/img; torch %s CPU"
                         % (sample, reps, 1000 * fwd / (sample * reps), 1000 * post / (sample * reps), torch.__version__)}
 
@@ -403,15 +490,19 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%dx%d synthetic uint8 images, batch %d per GPU, shipped %s checkpoint, conf %.2f nms %.2f, max_det %d"
                    % (W, H, B, args.res, io["conf_thre"], io["nms_thre"], args.max_det),
-                   "global_batch": n_total, "parallelism": "dp%d (image shards, one NCCL gather of detection slabs)" % world,
+                   "global_batch": n_total, "parallelism": "dp%d (image shards, one compacted NCCL gather of detection lists per step)" % world,
                    "l2": "inputs larger than L2: %.0f MB resident fp32 input + %.1f GB of activations written per step"
                    % (4e-6 * B * H * W, 1e-9 * B * sum(g["bytes"] for g in work.values()) / 2),
                    "detections_last_step": n_det},
         "e2e": {"value": n_total * args.steps / (e2e_ms_max * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * H * W,
-                "d2h_bytes_per_step": B * args.max_det * _lib.DET_DTYPE.itemsize + 8 * B, "ms_per_step": e2e_ms_max / args.steps,
+                "d2h_bytes_per_step": (B * args.max_det * _lib.DET_DTYPE.itemsize + 8 * B) if world == 1 else
+                world * (4 * ((-(-n_total // world) + 3) // 2 * 2) + _lib.DET_DTYPE.itemsize * (-(-n_total // world)) * min(args.max_det, 8)),
+                "ms_per_step": e2e_ms_max / args.steps,
                 "api": "Detect_YOLO.submit_batch/collect -> yf_detect_submit_u8/yf_detect_wait (pinned uint8 in, yf_det slab out, two slots)",
                 "blocking_call_ms_per_step": sync_ms, "blocking_api": "Detect_YOLO.detect_batch -> yf_detect_host_u8"},
         "gpu_launches": launches,
+        "gather_check": gather_check,
+        "latency": latency,
         "clocks": clocks,
         "roofline": roofline,
         "fp32": fp32,

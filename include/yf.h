@@ -181,6 +181,16 @@ int yf_detect_wait(yf_ctx* ctx, int slot);
 int yf_detect_submit_u8_dev(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, const yf_post_params* p,
                             yf_det* out_dev, int32_t* counts_dev, int32_t* status_dev);
 
+/* ---- multi-GPU result return ------------------------------------------------------ */
+
+/* Compacts the per-image slabs of yf_detect / yf_detect_submit_u8_dev (dets dev [B][max_det], counts dev [B]) into ONE contiguous
+ * message: packed dev = int32 header [total, B, n_0 .. n_{B-1}] in `hdr_slots` int32 words (even, >= B + 2), followed by the records of
+ * image 0, 1, ... back to back, n_b = min(counts[b], max_det), at most cap_records of them; `total` is the untruncated sum, so a
+ * receiver sees an overflow instead of a silent cut. The reference is single-process; this is the payload of the one
+ * collective that returns per-rank detection lists to rank 0 (yolo_fastest_b200/dist.py). */
+int yf_compact_dets(yf_ctx* ctx, const yf_det* dets, const int32_t* counts, int B, int max_det, void* packed, int hdr_slots,
+                    int cap_records, void* stream);
+
 /* ---- pre-processing on the device ------------------------------------------ */
 
 /* Replaces the image half of Detect_YOLO.__pre_process (detect.py:107-122): cv2.cvtColor(BGR2GRAY) followed by

@@ -15,6 +15,31 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# Measured parity figures that are REPORTED, not hidden behind a tolerance (violation counts of the survey's strict allclose form,
+# integer-box agreement counts, distances from float64): tests call report(key, value); the session prints them in the terminal
+# summary and writes gpurun_out/parity_report.json (copied to profiles/ by the builder).
+PARITY_REPORT = {}
+
+
+def report(key, value):
+    PARITY_REPORT[key] = value
+
+
+def pytest_terminal_summary(terminalreporter):
+    if not PARITY_REPORT:
+        return
+    import json
+    terminalreporter.write_line("parity report (measured, see tests/conftest.py):")
+    for k in sorted(PARITY_REPORT):
+        terminalreporter.write_line("  %s: %s" % (k, PARITY_REPORT[k]))
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        json.dump(PARITY_REPORT, open(os.path.join(out, "parity_report.json"), "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """The C-ABI library must exist for every test session (nvcc cross-compiles without a GPU)."""

@@ -10,9 +10,12 @@ import torch
 import yolo_fastest_b200 as yf
 from oracle import yolo_oracle as O
 
-from conftest import GOLD, rows_equal
+from conftest import GOLD, report, rows_equal
 
 pytestmark = pytest.mark.gpu
+
+
+KNOWN_PIXEL_FLIPS = {"256x320": 0, "512x640": 0}       # images (of 20) with a 1-pixel coordinate difference; measured on B200, see the report
 
 
 def _iou(a, b):
@@ -51,7 +54,11 @@ def test_shipped_images_end_to_end(gold, res):
             det.adjust_coord(rows)
             _match([list(r) for r in g["kept_adj_%02d" % i]], rows)
     assert flags == [bool(f) for f in g["has_targets"]]                  # the published detect / no-target pattern
-    assert exact >= len(names) - 1, "integer boxes differ on %d images" % (len(names) - exact)
+    # every box matched above at IoU > 0.99 with the same class; on how many images are the integer pixel coordinates identical too?
+    # (a coordinate is round(x -+ w/2) of float64 values computed from fp32 logits: a logit that differs in its last bits from the
+    # reference's can move a value across a .5 boundary). The count is measured and pinned, not allowed as slack.
+    report("integer-identical boxes %s" % res, "%d of %d images" % (exact, len(names)))
+    assert exact == len(names) - KNOWN_PIXEL_FLIPS[res], "integer boxes differ on %d images" % (len(names) - exact)
 
 
 @pytest.mark.parametrize("res", ["256x320", "512x640"])
@@ -120,13 +127,13 @@ def test_async_double_buffered_serving_loop(gold):
         det.submit_batch(g["u8"][:2], 0)            # not a host tensor
 
 
-def test_full_size_batch_256_properties(gold):
-    """BASELINE.json's headline configuration (640x512, batch 256) through the C ABI, checked by size-independent properties:
+@pytest.mark.parametrize("res", ["512x640", "256x320"])
+def test_full_size_batch_256_properties(gold, res):
+    """BASELINE.json's batch-256 configurations (640x512: the headline; 320x256: config 3) through the C ABI, checked by size-independent properties:
     image independence (the batch equals its four 64-image quarters and a permutation of itself, bit for bit), agreement of
     the blocking, asynchronous and device-resident entry points, and the oracle on a sample of the images (heads within 1e-4,
     detections box for box). The 256 inputs are the 20 shipped frames, each rolled by a different offset so every image differs
     and most of them have detections."""
-    res = "512x640"
     g = gold.res[res]
     det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_" + res), yf.config_for(res), None)
     base = g["u8"]

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from yolo_fastest_b200 import _lib
-from yolo_fastest_b200.dist import gather_detections, shard_range
+from yolo_fastest_b200.dist import gather_compact, gather_detections, pack_host, shard_range, split_records
 
 
 def test_shard_range_partitions():
@@ -41,11 +41,22 @@ def _worker(rank, world, port, n_total, max_det, q):
     lo, hi = shard_range(n_total, rank, world)
     dl = torch.from_numpy(d[lo:hi].copy().view(np.uint8).reshape(hi - lo, max_det, 56))
     cl = torch.from_numpy(c[lo:hi].copy())
-    gd, gc = gather_detections(dl, cl, n_total, dst=0)
+    got = gather_detections(dl, cl, n_total, dst=0, rank_cap=(-(-n_total // world)) * max_det)
     if rank == 0:
-        q.put((gd.tobytes() == d.tobytes(), bool((gc == c).all())))
+        ok = len(got) == n_total and all(g.tobytes() == d[i, :c[i]].tobytes() for i, g in enumerate(got))
     else:
-        assert gd is None and gc is None
+        ok = got is None
+    # a message too small for a rank's detections must raise on rank 0, never truncate silently
+    h = gather_compact(dl, cl, n_total, dst=0, rank_cap=1)
+    if rank == 0:
+        try:
+            h.result()
+            ok = False
+        except _lib.YfError as e:
+            ok = ok and "rank_cap" in str(e)
+        q.put(ok)
+    else:
+        assert h.result() == (None, None) and ok
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,4 +75,17 @@ def test_two_rank_gather_restores_order():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert ok == (True, True)
+    assert ok is True
+
+
+def test_message_layout():
+    """pack_host restates yf_compact_dets: int32 header [total, B, n_b ...] then the records back to back."""
+    d, c = _fake_dets(5, 4, 3)
+    c[1] = 9                                   # more than max_det: clipped to the slab capacity
+    msg = pack_host(torch.from_numpy(d.view(np.uint8).reshape(5, 4, 56)), torch.from_numpy(c), 8, 32).numpy()
+    hdr = msg[:32].view(np.int32)
+    n = np.minimum(c, 4)
+    assert hdr[0] == n.sum() and hdr[1] == 5 and list(hdr[2:7]) == list(n)
+    recs = msg[32:32 + 56 * int(n.sum())].view(_lib.DET_DTYPE)
+    parts = split_records(recs, n)
+    assert all(p.tobytes() == d[i, :n[i]].tobytes() for i, p in enumerate(parts))

@@ -7,6 +7,8 @@ import torch
 import yolo_fastest_b200 as yf
 from oracle import yolo_oracle as O
 
+from conftest import report
+
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 TAPS = ["conv1_4", "res1_1", "conv2_1", "res2_1", "res2_2", "conv3_1", "res3_1", "res3_2", "conv3_4", "res3_3", "res3_4",
@@ -30,13 +32,23 @@ def _close(got, ref, what, rel=TOL):
     assert torch.allclose(got, ref, rtol=rel, atol=rel * scale), "%s: allclose failed" % what
 
 
-def _check_heads(m, sd, x, what, rel=TOL):
-    """Two-sided criterion. (1) GPU vs the reference's fp32 result: within `rel` of the tensor scale.
-    (2) GPU vs the same network evaluated in float64: within 1e-5 of the tensor scale of exact arithmetic (a tenth of the
-    tolerance; measured on the trained networks: 3.5e-6 .. 5.4e-6, the reference's own fp32 result sits 1e-6 .. 1.3e-5 away,
-    tools/noise_floor.py, tools/ch3_probe.py), or - on the ill-conditioned stress networks, where fp32 itself is further away - no
-    further than 1.5x the reference's own distance. The GPU's extra distance on trained networks is the truncating accumulation
-    of the tensor core, bounded by keeping the accumulation chains short."""
+def _strict_violations(a, b):
+    """elements violating the survey's element-wise form allclose(rtol=1e-4, atol=1e-4)"""
+    return int(((a.double() - b.double()).abs() > 1e-4 + 1e-4 * b.double().abs()).sum())
+
+
+def _check_heads(m, sd, x, what, rel=TOL, key=None):
+    """north_star: raw fp32 head tensors within 1e-4. Three statements, all measured and the counts REPORTED (conftest.report):
+    (1) scale-relative: max|gpu - ref32| <= rel * max|ref32| with rel = 1e-4. On the ill-conditioned random-init stress network the
+        reference's OWN fp32 result sits 5e-5 .. 7e-5 of scale from exact arithmetic (profiles/r02_stress_error_growth.txt: the
+        GPU tracks that distance tap by tap, on the tensor-core and on the pure-FFMA library alike), so two correct fp32
+        evaluations differ by up to ~1e-4; there the bound is max(1e-4, 2 x the reference's own distance from float64).
+    (2) against float64: the GPU is no further from exact arithmetic than 1.5x the reference's own fp32 result (+2e-6 of scale),
+        or within 1e-5 of scale.
+    (3) the survey's element-wise form allclose(rtol=1e-4, atol=1e-4): the reference itself violates it against float64 (300 of
+        153 600 head_large elements at 512x640), so it cannot hold between two independent fp32 evaluations; asserted is that the
+        GPU-vs-ref32 violation count stays within the count expected from two independent roundings of the reference's own size
+        (<= 6 x the ref32-vs-float64 count + 0.05% of the elements), and both counts are reported."""
     sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
     ref32 = O.forward(sd, x)
     ref64 = O.forward(sd64, x.double())
@@ -44,12 +56,22 @@ def _check_heads(m, sd, x, what, rel=TOL):
     for h, name in enumerate(("head_large", "head_small")):
         g = got[h].cpu()
         assert g.shape == ref32[h].shape
-        _close(g, ref32[h], "%s %s" % (what, name), rel)
         scale = ref64[h].abs().max().item()
         e_ref = (ref32[h].double() - ref64[h]).abs().max().item()
         e_gpu = (g.double() - ref64[h]).abs().max().item()
+        e_gr = (g.double() - ref32[h].double()).abs().max().item()
+        bound = max(rel, 2.0 * e_ref / scale)
+        v_gpu, v_ref = _strict_violations(g, ref32[h]), _strict_violations(ref32[h], ref64[h])
+        if key:
+            report("%s %s" % (key, name), {"gpu-ref32 / scale": "%.3e" % (e_gr / scale), "gpu-fp64 / scale": "%.3e" % (e_gpu / scale),
+                                          "ref32-fp64 / scale": "%.3e" % (e_ref / scale), "bound": "%.3e" % bound,
+                                          "allclose(1e-4,1e-4) violations gpu-vs-ref32": "%d/%d" % (v_gpu, g.numel()),
+                                          "violations ref32-vs-fp64": "%d/%d" % (v_ref, g.numel())})
+        assert e_gr <= bound * scale, "%s %s: max|gpu-ref32|/scale = %.3g > %.3g (ref32 is %.3g from fp64)" % (what, name, e_gr / scale, bound, e_ref / scale)
         assert e_gpu <= max(1.5 * e_ref + 2e-6 * scale, 1e-5 * scale), \
             "%s %s: gpu is %.3g from fp64 (scale %.3g), the reference only %.3g" % (what, name, e_gpu, scale, e_ref)
+        assert v_gpu <= 6 * v_ref + 0.0005 * g.numel(), \
+            "%s %s: %d elements violate allclose(1e-4,1e-4) against ref32; the reference itself violates it %d times against fp64" % (what, name, v_gpu, v_ref)
     return got, ref32
 
 
@@ -63,7 +85,7 @@ def test_heads_on_shipped_images(gold, res):
     sd = gold.sd("yolo_fastest_" + res)
     m = _model(sd, 3)
     x = torch.cat([O.preprocess_gray(u) for u in g["u8"]], 0)
-    (hl, hs), _ = _check_heads(m, sd, x, "shipped images")
+    (hl, hs), _ = _check_heads(m, sd, x, "shipped images", key="shipped images " + res)
     n = len(g["head_large"])
     _close(hl[:n], torch.from_numpy(g["head_large"]), "head_large vs golden")
     _close(hs[:n], torch.from_numpy(g["head_small"]), "head_small vs golden")
@@ -101,10 +123,10 @@ def test_golden_synthetic_heads(gold):
 def test_other_shapes_80_classes(gold, H, W, B):
     """Ragged sizes (maps that do not fill a tile, odd map widths 13/11/3/1) and the 255-channel heads.
     The calibrated random-init network amplifies rounding noise ~5x more than the trained ones (the reference's
-    own fp32 result sits 7e-5 of scale from fp64 here), hence 3e-4 against ref32; the fp64 criterion is unchanged."""
+    own fp32 result sits 5e-5 .. 7e-5 of scale from fp64 here): _check_heads states the bound in terms of that distance."""
     sd = gold.sd("stress80_416")
     m = _model(sd, 80)
-    _check_heads(m, sd, _rand_x(B, H, W, 17), "80-class %dx%d" % (H, W), rel=3e-4)
+    _check_heads(m, sd, _rand_x(B, H, W, 17), "80-class %dx%d" % (H, W), key="stress80 %dx%d b%d" % (H, W, B))
 
 
 def test_stress_golden_heads(gold):
@@ -113,9 +135,9 @@ def test_stress_golden_heads(gold):
     m = _model(sd, 80)
     u8 = torch.randint(0, 256, (2, 416, 416), generator=torch.Generator().manual_seed(int(g["u8_seed"])), dtype=torch.uint8).numpy()
     x = torch.cat([O.preprocess_gray(s) for s in u8], 0)
-    (hl, hs), _ = _check_heads(m, sd, x, "stress", rel=3e-4)
-    _close(hl, torch.from_numpy(g["head_large"]), "stress head_large vs golden", rel=3e-4)
-    _close(hs, torch.from_numpy(g["head_small"]), "stress head_small vs golden", rel=3e-4)
+    (hl, hs), _ = _check_heads(m, sd, x, "stress", key="stress80 golden")
+    _close(hl, torch.from_numpy(g["head_large"]), "stress head_large vs golden", rel=1.5e-4)      # golden = ref32; bound 2 x (ref32 - fp64) = 1.4e-4
+    _close(hs, torch.from_numpy(g["head_small"]), "stress head_small vs golden", rel=1.5e-4)
 
 
 def test_batch_growth_reload_and_linearity_in_batch(gold):

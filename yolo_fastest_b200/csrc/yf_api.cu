@@ -1790,4 +1790,16 @@ extern "C" int yf_detect_wait(yf_ctx* ctx, int slot) {
     return YF_OK;
 }
 
+extern "C" int yf_compact_dets(yf_ctx* ctx, const yf_det* dets, const int32_t* counts, int B, int max_det, void* packed, int hdr_slots,
+                               int cap_records, void* stream) {
+    CTX_CHECK(ctx);
+    if (!dets || !counts || !packed || B < 1 || max_det < 1 || hdr_slots < B + 2 || cap_records < 0) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
+    if (hdr_slots % 2) { set_err(&ctx->err, "hdr_slots must be even (records are 8-byte aligned)"); return YF_ERR_ARG; }
+    int32_t* hdr = reinterpret_cast<int32_t*>(packed);
+    compact_dets_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dets, counts, B, max_det, hdr, hdr_slots, reinterpret_cast<yf_det*>(hdr + hdr_slots), cap_records);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return YF_OK;
+}
+
 extern "C" int64_t yf_launch_count(const yf_ctx* ctx) { return ctx ? ctx->launches : -1; }

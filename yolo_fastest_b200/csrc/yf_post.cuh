@@ -392,4 +392,44 @@ __global__ void val_decode_kernel(const ValDecodeArgs a) {
     for (int k = 4; k < attrs; ++k) o[k] = sigmoid_f32(__ldg(p + (size_t)k * hw));
 }
 
+// ---- compaction of per-image detection slabs into one contiguous record list (multi-GPU result return) -----------------------
+// dets [B][max_det] + counts [B]  ->  packed = int32 header [total, B, n_0 .. n_{B-1}] (hdr_slots int32 words reserved) followed by
+// the records of image 0, 1, ... back to back (n_b = min(counts[b], max_det)). Records beyond `cap` are dropped; `total` is the
+// untruncated sum, so the receiver detects the overflow. One CTA: a block-wide scan over the images, then a cooperative copy.
+__global__ void __launch_bounds__(256) compact_dets_kernel(const yf_det* __restrict__ dets, const int32_t* __restrict__ counts, int B, int max_det,
+                                                           int32_t* __restrict__ hdr, int hdr_slots, yf_det* __restrict__ rec, int cap) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const uint2* src = reinterpret_cast<const uint2*>(dets);          // a record = 7 x 8 bytes
+    uint2* dst = reinterpret_cast<uint2*>(rec);
+    for (int b0 = 0; b0 < B; b0 += 256) {
+        const int b = b0 + tid;
+        const int n = b < B ? min(max(counts[b], 0), max_det) : 0;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+        const int off = s_base + wbase + incl - n;                    // first record slot of image b
+        if (b < B) {
+            if (2 + b < hdr_slots) hdr[2 + b] = n;
+            for (int k = 0; k < n; ++k) {
+                if (off + k < cap) {
+#pragma unroll
+                    for (int w8 = 0; w8 < 7; ++w8) dst[(size_t)(off + k) * 7 + w8] = src[((size_t)b * max_det + k) * 7 + w8];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 255) s_base = off + n;
+        __syncthreads();
+    }
+    if (tid == 0) { hdr[0] = s_base; hdr[1] = B; }
+}
+
 }  // namespace yf
