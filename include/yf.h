@@ -56,6 +56,11 @@ typedef struct {
     int32_t src;
 } yf_det; /* 56 bytes */
 
+/* Model variants. YF_VARIANT_LITE = the reference's YoloFastest_lite (yolo_fastest.py:234-372): the same parameter set
+ * with heads of (num_anchors * num_cls) * (5 + num_cls) channels (:240-241), a forward that goes conv3_2 -> conv3_4 without the depthwise
+ * conv3_3 (:335-337) and ends at head_5 (:365-372): yf_forward then writes head_small only (head_large may be NULL). */
+enum { YF_VARIANT_FULL = 0, YF_VARIANT_LITE = 1 };
+
 enum { YF_MODE_DETECT = 0,   /* src/detect.py:41-84,155-169 */
        YF_MODE_VALIDATE = 1  /* src/model_training/loss/yolo_loss.py:98-141 + utils/general.py:87-143 */ };
 
@@ -67,12 +72,17 @@ enum { YF_MODE_DETECT = 0,   /* src/detect.py:41-84,155-169 */
  * (_config.py:11).  Head shapes follow: large = [B, A*(5+nc), H/16, W/16], small = [.., H/32, W/32]. */
 int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors,
               int max_batch, int H, int W);
+/* The same for a model variant: YF_VARIANT_FULL == yf_create; YF_VARIANT_LITE replaces YoloFastest_lite(io_params)
+ * (yolo_fastest.py:234-319), single-channel input. */
+int yf_create_variant(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors,
+                      int max_batch, int H, int W, int variant);
 void yf_destroy(yf_ctx* ctx);
 const char* yf_last_error(const yf_ctx* ctx);
 int yf_abi_version(void);
 
 /* Number of floats yf_load_weights expects for this architecture (host-side helper, no CUDA). */
 int64_t yf_weight_count(int in_ch, int num_cls, int num_anchors);
+int64_t yf_weight_count_variant(int in_ch, int num_cls, int num_anchors, int variant);
 
 /* Replaces model.load_state_dict(torch.load(path)) + .eval() (detect.py:89-91).
  * `host_blob`: BatchNorm-folded fp32 parameters in forward order, per conv its weight in PyTorch

@@ -10,6 +10,7 @@ It restates, on the CPU, the algorithm of the reference path (citations are
 relative to the reference repo root):
 
 * ``forward``            <- src/model_training/model/yolo_fastest.py:16-66,150-218
+* ``forward_lite``       <- src/model_training/model/yolo_fastest.py:321-372 (YoloFastest_lite.forward)
 * ``decode_box``         <- src/detect.py:23-25,41-67
 * ``cal_iou`` / ``nms``  <- src/detect.py:27-39,69-84
 * ``detect_postprocess`` <- src/detect.py:155-169  (class split, stable sort, per-class NMS)
@@ -114,6 +115,38 @@ def forward(sd, x, taps=None):
             x = tap(name, _layer(sd, name, x))
         head_large = F.conv2d(x, sd["head_4.weight"], sd["head_4.bias"])                      # :148,216
     return head_large, head_small
+
+
+def forward_lite(sd, x, taps=None):
+    """YoloFastest_lite.forward (yolo_fastest.py:321-372) -> head_5. Same layers as `forward` with conv3_3 SKIPPED (the lite forward
+    goes conv3_2 -> conv3_4, :335-337) and nothing after head_5 (:365-372)."""
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t
+        return t
+
+    with torch.no_grad():
+        for name in _TRUNK + ["conv4_2"] + _TRUNK5 + ["conv5_2", "conv5_3", "conv5_4", "conv5_5", "conv5_6"]:
+            if name == "conv3_3":
+                continue
+            x = _res(sd, name, x) if name.startswith("res") else _layer(sd, name, x)
+            tap(name, x)
+        return F.conv2d(x, sd["head_5.weight"], sd["head_5.bias"])
+
+
+def lite_state_dict(sd, num_cls=3, num_anchors=3):
+    """A YoloFastest_lite state_dict derived from a shipped YoloFastest checkpoint: every layer is shape-compatible except the two
+    head convs, whose (num_anchors * num_cls) * (5 + num_cls) outputs (yolo_fastest.py:240-241) are the shipped head rows repeated
+    with deterministic per-copy gains, so the network stays trained-like. The reference ships no lite checkpoint."""
+    out = dict(sd)
+    nout = num_anchors * num_cls * (5 + num_cls)
+    for h in ("head_5", "head_4"):
+        w, b = sd[h + ".weight"], sd[h + ".bias"]
+        reps = -(-nout // w.shape[0])
+        gains = torch.linspace(1.0, 0.5, reps).repeat_interleave(w.shape[0])[:nout]
+        out[h + ".weight"] = (w.repeat(reps, 1, 1, 1)[:nout] * gains.view(-1, 1, 1, 1)).contiguous()
+        out[h + ".bias"] = (b.repeat(reps)[:nout] * gains).contiguous()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -77,6 +77,8 @@ def test_detect_batch_host_buffers(gold, res):
     for B in (1, 7):
         part = det.detect_batch(u8[:B], max_det=16)
         assert part == rows[:B]
+    # a capacity smaller than an image's list is never a silent cut: the batch is run again with room for every detection
+    assert max(len(r) for r in rows) >= 2 and det.detect_batch(u8, max_det=1) == rows
 
 
 def test_batch_detect_driver(gold, tmp_path):

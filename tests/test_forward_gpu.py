@@ -1,5 +1,7 @@
 """yf_forward (through the drop-in YoloFastest) against the CPU oracle: raw fp32 head tensors within 1e-4
 (allclose rtol=atol=1e-4 AND max|d|/max|ref| <= 1e-4 — SURVEY.md §7.3-1), plus every tapped group output."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -208,3 +210,27 @@ def test_three_channel_input(gold, H, W, B):
     _check_heads(m, sd, x, "3-channel %dx%d" % (H, W))
     with pytest.raises(yf.YfError):
         m(x[:, :1].cuda())                          # a gray batch is rejected, not broadcast
+
+
+@pytest.mark.parametrize("H,W,B", [(256, 320, 2), (96, 352, 1), (512, 640, 3)])
+def test_yolo_fastest_lite(gold, H, W, B):
+    """YoloFastest_lite (yolo_fastest.py:234-372): single head, conv3_3 skipped, (A*nc)*(5+nc) head channels —
+    every tapped group and the head against the oracle, and the head against the reference's own output where it is frozen."""
+    sd = O.lite_state_dict(gold.sd("yolo_fastest_256x320"))
+    m = yf.YoloFastest_lite({"num_cls": 3, "input_channel": 1, "num_anchors": 3})
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = (torch.randint(0, 256, (B, 1, H, W), generator=torch.Generator().manual_seed(41)).float() - 128.0) / 255.0
+    taps = {}
+    want = O.forward_lite(sd, x, taps)
+    got = m(x.cuda())
+    assert got.shape == (B, 72, H // 32, W // 32)
+    for name in TAPS:
+        if name in ("conv4_1_1", "conv4_1_3"):
+            continue                                   # the lite forward ends at head_5
+        _close(m.tap(name, B).view(taps[name].shape), taps[name], "lite " + name)
+    _close(got, want, "lite head_5")
+    g = np.load(os.path.join(gold.dir, "golden_lite.npz"))
+    for tag in ("a", "b"):
+        if [B, H, W] == [int(v) for v in g["shape_" + tag]]:
+            _close(got, torch.from_numpy(g["head_" + tag]), "lite head_5 vs the reference's frozen output")

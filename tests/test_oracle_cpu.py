@@ -1,5 +1,7 @@
 """The oracle against the golden vectors frozen from the reference (tests/golden/make_golden.py) and
 against the facts the reference publishes.  CPU only."""
+import os
+
 import numpy as np
 import torch
 
@@ -134,3 +136,14 @@ def test_decode_overflow_domain():
     except OverflowError:
         raised = True
     assert raised
+
+
+def test_lite_oracle_matches_reference_golden(gold):
+    """oracle.forward_lite against the unmodified reference's YoloFastest_lite outputs (tests/golden/make_golden_lite.py)."""
+    g = np.load(os.path.join(gold.dir, "golden_lite.npz"))
+    sd = O.lite_state_dict(gold.sd("yolo_fastest_256x320"))
+    assert sd["head_5.weight"].shape == (72, 128, 1, 1) and sd["head_4.weight"].shape == (72, 96, 1, 1)
+    for tag in ("a", "b"):
+        B, H, W = (int(v) for v in g["shape_" + tag])
+        x = (torch.randint(0, 256, (B, 1, H, W), generator=torch.Generator().manual_seed(int(g["seed"]))).float() - 128.0) / 255.0
+        assert torch.equal(O.forward_lite(sd, x), torch.from_numpy(g["head_" + tag]))

@@ -129,10 +129,26 @@ def test_synthetic_heads_batch(gold):
         want = O.detect_postprocess((hl, hs), io["anchors"], io["input_shape"], io["conf_thre"], io["nms_thre"], 3, 3, batch_index=b)
         rows_equal(want, got[b], conf_tol=1e-12)
     assert got[3] == [] and dec[3] == []
-    # truncation: counts report the true number, the slab holds the first max_det rows in output order
-    raw = pp.postprocess_batch((hl.cuda(), hs.cuda()), max_det=5)
+    # no silent truncation: an explicit capacity that some image exceeds raises (the reference's lists have no cap); the default
+    # call above started from 256 slots per image and was repeated with the exact size (these images hold ~600 candidates each)
+    assert max(len(d) for d in dec) > pp.DEFAULT_CAP
+    with pytest.raises(yf.YfError):
+        pp.postprocess_batch((hl.cuda(), hs.cuda()), max_det=5)
+    # the C ABI itself reports the true count and fills the slab with the first max_det rows in output order
+    ctx = pp._context(torch.device("cuda:0"), 16)
+    out = torch.empty((16, 5, 56), dtype=torch.uint8, device="cuda")
+    cnt = torch.empty(16, dtype=torch.int32, device="cuda")
+    st = torch.empty(16, dtype=torch.int32, device="cuda")
+    p = pp._params(_lib.MODE_DETECT, 5)
+    a, b_ = hl.cuda().contiguous(), hs.cuda().contiguous()
+    _lib.check(_lib.lib().yf_postprocess(ctx.handle, a.data_ptr(), b_.data_ptr(), 16, 16, 20, 8, 10, C.byref(p), out.data_ptr(), cnt.data_ptr(),
+                                         st.data_ptr(), None), ctx.handle)
+    torch.cuda.synchronize()
+    slab = out.cpu().numpy().view(_lib.DET_DTYPE).reshape(16, 5)
+    from yolo_fastest_b200.detector import _rows_from_dets
     for b in range(16):
-        rows_equal(got[b][:5], raw[b])
+        assert int(cnt[b]) == len(got[b])
+        rows_equal(got[b][:5], _rows_from_dets(slab[b, :min(5, len(got[b]))]))
 
 
 def test_validation_flavour_from_heads_and_rows(gold):
@@ -185,7 +201,9 @@ def test_status_flags():
     hl[0, 4, 0, 0] = 5.0
     hl[0, 2, 0, 0] = 30.0                       # exp(30) * anchor >> 2^25
     hl[1, 4, 1, 1] = float("nan")
-    _, _, status = pp._run((hl.cuda(), hs.cuda()), nms=True)
+    _, _, status = pp._run((hl.cuda(), hs.cuda()), nms=True, check_status=False)
     assert status[0] & 1 and status[1] & 2
     with pytest.raises(yf.YfError):
         pp.postprocess_batch((hl.cuda(), hs.cuda()))
+    with pytest.raises(yf.YfError):                 # the decode-only calls check the domain flag too
+        pp.decode_box_batch((hl.cuda(), hs.cuda()))

@@ -10,6 +10,8 @@ LIB_PATH = os.environ.get("YF_B200_LIB", os.path.join(_HERE, "libyf_b200.so"))  
 YF_MAX_ANCHORS = 8
 MODE_DETECT = 0
 MODE_VALIDATE = 1
+VARIANT_FULL = 0
+VARIANT_LITE = 1
 
 
 class YfError(RuntimeError):
@@ -36,10 +38,12 @@ class YfPostParams(C.Structure):
 _P = C.c_void_p
 SYMBOLS = [
     ("yf_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("yf_create_variant", C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("yf_destroy", None, [_P]),
     ("yf_last_error", C.c_char_p, [_P]),
     ("yf_abi_version", C.c_int, []),
     ("yf_weight_count", C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    ("yf_weight_count_variant", C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     ("yf_load_weights", C.c_int, [_P, _P, C.c_int64]),
     ("yf_forward", C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     ("yf_tap", C.c_int, [_P, C.c_char_p, C.c_int, _P, C.POINTER(C.c_int64), _P]),
@@ -108,14 +112,16 @@ def make_params(anchors, conf_thres, nms_thres, input_h, input_w, mode, max_det)
 class Ctx:
     """Owner of one yf_ctx (one device, one input size, a maximum batch)."""
 
-    def __init__(self, device_index, in_ch, num_cls, num_anchors, max_batch, H, W):
+    def __init__(self, device_index, in_ch, num_cls, num_anchors, max_batch, H, W, variant=0):
         self.handle = _P()
+        self.variant = variant
         self.device_index, self.in_ch, self.num_cls, self.num_anchors = device_index, in_ch, num_cls, num_anchors
         self.max_batch, self.H, self.W = max_batch, H, W
         self.nout = num_anchors * (5 + num_cls)
         self.ncand = num_anchors * ((H // 16) * (W // 16) + (H // 32) * (W // 32))
+        self.pending = set()          # slots of the asynchronous path holding a submitted, not yet collected batch
         l = lib()
-        check(l.yf_create(C.byref(self.handle), device_index, in_ch, num_cls, num_anchors, max_batch, H, W), None)
+        check(l.yf_create_variant(C.byref(self.handle), device_index, in_ch, num_cls, num_anchors, max_batch, H, W, variant), None)
 
     def close(self):
         if self.handle:

@@ -59,9 +59,15 @@ struct SpecTable {
     const Spec& get(const std::string& name) const { return specs[index.at(name)]; }
 };
 
-SpecTable build_specs(int in_ch, int num_cls, int num_anchors) {
+// head channels: YoloFastest has num_anchors * (5 + num_cls) (yolo_fastest.py:74-75); YoloFastest_lite multiplies its anchor count
+// by the class count first (yolo_fastest.py:240-241)
+int head_channels(int num_cls, int num_anchors, int variant) {
+    return (variant == YF_VARIANT_LITE ? num_anchors * num_cls : num_anchors) * (5 + num_cls);
+}
+
+SpecTable build_specs(int in_ch, int num_cls, int num_anchors, int variant = 0) {
     SpecTable t;
-    const int nout = num_anchors * (5 + num_cls);
+    const int nout = head_channels(num_cls, num_anchors, variant);
     t.add("conv0", in_ch, 8, 3);
     t.add("conv1_2", 8, 8, 1); t.add("conv1_3", 8, 8, 3, 8); t.add("conv1_4", 8, 4, 1);
     t.irb("res1_1", 4, 8);
@@ -137,6 +143,7 @@ struct Group {
 };
 
 struct yf_ctx {
+    int variant = 0;                                    // YF_VARIANT_FULL / YF_VARIANT_LITE
     int device = 0, in_ch = 1, num_cls = 3, num_anchors = 3, max_batch = 1, H = 0, W = 0;
     int nout = 0;
     bool weights_loaded = false;
@@ -303,6 +310,7 @@ using CfgRes5 = YF_CFGRES5;
 #define YF_CFGPW52 PwCfg<48, 96, 80, 8, 256, true>
 #endif
 using CfgPw52 = YF_CFGPW52;
+using CfgLite34 = PwPwCfg<8, 48, 16, 128>;          // YoloFastest_lite: conv3_2 -> conv3_4 without the depthwise conv3_3
 #ifndef YF_CFGNECKS1
 #define YF_CFGNECKS1 IrbCfg<96, 96, 128, 5, 1, 8, 20, 48, 4, 8, 4, 640, 1, false, false, false, false>
 #endif
@@ -573,6 +581,13 @@ void launch_pw52(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) 
     const int HW = g.Hin * g.Win;
     const int tiles = cdiv(HW, C::PIXT);
     pw_kernel<C><<<B * tiles, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, HW, tiles);
+}
+void launch_lite34(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using C = CfgLite34;
+    const int HW = g.Hin * g.Win;
+    const long long groups = (long long)B * (HW / 4);
+    const int grid = (int)std::min<long long>((groups + C::NT - 1) / C::NT, (long long)g.nsm * 8);
+    pwpw_kernel<C><<<grid, C::NT, 0, st>>>(g.x, g.y, g.w, HW, groups);
 }
 void launch_upcat(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using C = CfgUpCat;
@@ -913,6 +928,21 @@ int64_t pack_dense(std::vector<float>& out, const Folded& f) {
     return off;
 }
 
+int64_t pack_lite34(std::vector<float>& out, const Folded& f) {
+    using C = CfgLite34;
+    pad4(out);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int m = 0; m < C::M; ++m) {
+        for (int k = 0; k < C::K; ++k) o[C::OFF_W1 + k * C::M + m] = f.w("conv3_2")[m * C::K + k];
+        o[C::OFF_B1 + m] = f.b("conv3_2")[m];
+        for (int n = 0; n < C::N; ++n) o[C::OFF_W2 + m * C::N + n] = f.w("conv3_4")[n * C::M + m];
+    }
+    for (int n = 0; n < C::N; ++n) o[C::OFF_B2 + n] = f.b("conv3_4")[n];
+    return off;
+}
+
 int64_t pack_pw52(std::vector<float>& out, const Folded& f) {
     using C = CfgPw52;
     pad4(out);
@@ -1005,12 +1035,32 @@ extern "C" int yf_abi_version(void) { return YF_ABI_VERSION; }
 
 extern "C" const char* yf_last_error(const yf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
-extern "C" int64_t yf_weight_count(int in_ch, int num_cls, int num_anchors) {
-    if (in_ch < 1 || num_cls < 1 || num_anchors < 1) return -1;
-    return build_specs(in_ch, num_cls, num_anchors).total;
+extern "C" int64_t yf_weight_count_variant(int in_ch, int num_cls, int num_anchors, int variant) {
+    if (in_ch < 1 || num_cls < 1 || num_anchors < 1 || (variant != YF_VARIANT_FULL && variant != YF_VARIANT_LITE)) return -1;
+    return build_specs(in_ch, num_cls, num_anchors, variant).total;
+}
+extern "C" int64_t yf_weight_count(int in_ch, int num_cls, int num_anchors) { return yf_weight_count_variant(in_ch, num_cls, num_anchors, YF_VARIANT_FULL); }
+
+// Post-processing workspace: everything a ctx needs for yf_postprocess / yf_decode / yf_val_nms / yf_nms_sorted_*. Allocated at
+// creation; the forward's activation, head and staging buffers (2 GB at 640x512, batch 256) come with the first yf_load_weights, so
+// a context that only ever post-processes (YOLO_post_process, val.non_max_suppression) stays small.
+static int alloc_post(yf_ctx* ctx) {
+    const int B = ctx->max_batch, H = ctx->H, W = ctx->W;
+    CU(cudaMalloc(&ctx->d_counts, sizeof(int32_t) * B));
+    CU(cudaMalloc(&ctx->d_status, sizeof(int32_t) * B));
+    ctx->NC = ctx->num_anchors * ((H / 16) * (W / 16) + (H / 32) * (W / 32));
+    const size_t n = (size_t)ctx->NC * B;
+    CU(cudaMalloc(&ctx->p_rec, sizeof(yf_det) * n));
+    CU(cudaMalloc(&ctx->p_conf, sizeof(double) * n));
+    CU(cudaMalloc(&ctx->p_cls, sizeof(int32_t) * n));
+    CU(cudaMalloc(&ctx->p_sbox, sizeof(int4) * n));
+    CU(cudaMalloc(&ctx->p_order, sizeof(int32_t) * n));
+    CU(cudaMalloc(&ctx->p_alive, n));
+    return YF_OK;
 }
 
-static int alloc_all(yf_ctx* ctx) {
+static int alloc_forward(yf_ctx* ctx) {
+    if (!ctx->d_act.empty()) return YF_OK;
     const int B = ctx->max_batch, H = ctx->H, W = ctx->W;
     auto dim = [&](int div, int& h, int& w) { h = H / div; w = W / div; };
     // (name, channels, divisor) of every group output, in launch order
@@ -1040,16 +1090,6 @@ static int alloc_all(yf_ctx* ctx) {
     CU(cudaMalloc(&ctx->d_hs, sizeof(float) * hs * B));
     CU(cudaMalloc(&ctx->d_x, sizeof(float) * (int64_t)ctx->in_ch * H * W * B));
     CU(cudaMalloc(&ctx->d_u8, (size_t)ctx->in_ch * H * W * B));
-    CU(cudaMalloc(&ctx->d_counts, sizeof(int32_t) * B));
-    CU(cudaMalloc(&ctx->d_status, sizeof(int32_t) * B));
-    ctx->NC = ctx->num_anchors * ((H / 16) * (W / 16) + (H / 32) * (W / 32));
-    const size_t n = (size_t)ctx->NC * B;
-    CU(cudaMalloc(&ctx->p_rec, sizeof(yf_det) * n));
-    CU(cudaMalloc(&ctx->p_conf, sizeof(double) * n));
-    CU(cudaMalloc(&ctx->p_cls, sizeof(int32_t) * n));
-    CU(cudaMalloc(&ctx->p_sbox, sizeof(int4) * n));
-    CU(cudaMalloc(&ctx->p_order, sizeof(int32_t) * n));
-    CU(cudaMalloc(&ctx->p_alive, n));
     return YF_OK;
 }
 
@@ -1109,7 +1149,8 @@ static void build_plan(yf_ctx* ctx) {
 #endif
     chain(make_irb<CfgRes3a>("res3_1", 8), 8, 8);
     chain(make_irb<CfgRes3a>("res3_2", 8), 8, 8);
-    chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
+    if (ctx->variant == YF_VARIANT_LITE) { Group g{}; g.name = "conv3_4"; g.launch = &launch_lite34; g.out_ch = 16; chain(g, 8, 8); }
+    else chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
 #if YF_USE_TC
     { Group g = make_irbtc<CfgRes3bTc>("res3_3", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
     { Group g = make_irbtc<CfgRes3bTc>("res3_4", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
@@ -1160,6 +1201,7 @@ static void build_plan(yf_ctx* ctx) {
         if (heads_on_tc(ctx->nout)) g.launch = &launch_dwpwtc_auto<CfgNeckS2Tc, CfgNeckS2TcS, CfgNeckS2TcN>;
         hw(g, 32, 32); g.a.x = prev; g.a.headn = ctx->nout; G.push_back(g);
     }
+    if (ctx->variant == YF_VARIANT_LITE) return;        // the lite forward ends at head_5 (yolo_fastest.py:365-372)
     {
         Group g{}; g.name = "conv4_1_1"; g.out_ch = 96;
         if (upcat_on_tc(ctx->H, ctx->W)) { g.launch = &launch_upcat_tc; g.occupancy = &occ_upcat_tc; }
@@ -1189,8 +1231,14 @@ static void set_sm_count(yf_ctx* ctx) {
 }
 
 extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors, int max_batch, int H, int W) {
+    return yf_create_variant(out, device, in_ch, num_cls, num_anchors, max_batch, H, W, YF_VARIANT_FULL);
+}
+
+extern "C" int yf_create_variant(yf_ctx** out, int device, int in_ch, int num_cls, int num_anchors, int max_batch, int H, int W, int variant) {
     if (!out) { set_err(nullptr, "out is null"); return YF_ERR_ARG; }
     *out = nullptr;
+    if (variant != YF_VARIANT_FULL && variant != YF_VARIANT_LITE) { set_err(nullptr, "unknown model variant %d", variant); return YF_ERR_ARG; }
+    if (variant == YF_VARIANT_LITE && in_ch != 1) { set_err(nullptr, "YoloFastest_lite is served for single-channel input"); return YF_ERR_ARG; }
     if (in_ch != 1 && in_ch != 3) { set_err(nullptr, "in_ch=%d unsupported: 1 (the shipped models, _config.py:10) or 3 (colour input)", in_ch); return YF_ERR_ARG; }
     if (num_cls < 1 || num_cls > POST_MAX_CLS || num_anchors < 1 || num_anchors > YF_MAX_ANCHORS || max_batch < 1) {
         set_err(nullptr, "bad num_cls/num_anchors/max_batch (%d, %d, %d)", num_cls, num_anchors, max_batch);
@@ -1206,9 +1254,9 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
     }
     yf_ctx* ctx = new yf_ctx();
     ctx->device = device; ctx->in_ch = in_ch; ctx->num_cls = num_cls; ctx->num_anchors = num_anchors;
-    ctx->max_batch = max_batch; ctx->H = H; ctx->W = W;
-    ctx->nout = num_anchors * (5 + num_cls);
-    ctx->specs = build_specs(in_ch, num_cls, num_anchors);
+    ctx->max_batch = max_batch; ctx->H = H; ctx->W = W; ctx->variant = variant;
+    ctx->nout = head_channels(num_cls, num_anchors, variant);
+    ctx->specs = build_specs(in_ch, num_cls, num_anchors, variant);
     auto fail = [&](int rc) { g_err = ctx->err; yf_destroy(ctx); return rc; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) { set_err(&ctx->err, "cudaSetDevice: %s", cudaGetErrorString(e)); return fail(YF_ERR_CUDA); }
     cudaError_t ie[] = {
@@ -1228,10 +1276,8 @@ extern "C" int yf_create(yf_ctx** out, int device, int in_ch, int num_cls, int n
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
-    int rc = alloc_all(ctx);
+    int rc = alloc_post(ctx);
     if (rc != YF_OK) return fail(rc);
-    build_plan(ctx);
-    set_sm_count(ctx);
     *out = ctx;
     return YF_OK;
 }
@@ -1269,6 +1315,12 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     for (int64_t i = 0; i < n_floats; ++i)
         if (!std::isfinite(host_blob[i])) { set_err(&ctx->err, "non-finite weight at %lld", (long long)i); return YF_ERR_ARG; }
     CU(cudaSetDevice(ctx->device));
+    if (ctx->groups.empty()) {                      // first weights: the forward's buffers and launch plan come into being now
+        int rc = alloc_forward(ctx);
+        if (rc != YF_OK) return rc;
+        build_plan(ctx);
+        set_sm_count(ctx);
+    }
     Folded f{host_blob, &ctx->specs};
     std::vector<float>& P = ctx->host_packed;
     P.clear();
@@ -1293,7 +1345,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     offs.push_back(pack_irb<CfgDown2>(P, f, "conv2_2", "conv2_3", "conv3_1", "", 0));
 #endif
     res(CfgRes3a{}, "res3_1"); res(CfgRes3a{}, "res3_2");
-    offs.push_back(pack_irb<CfgWide3>(P, f, "conv3_2", "conv3_3", "conv3_4", "", 0));
+    offs.push_back(ctx->variant == YF_VARIANT_LITE ? pack_lite34(P, f) : pack_irb<CfgWide3>(P, f, "conv3_2", "conv3_3", "conv3_4", "", 0));
 #if YF_USE_TC
     for (const char* n : {"res3_3", "res3_4", "res3_5", "res3_6"})
         offs.push_back(pack_irbtc<CfgRes3bTc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
@@ -1322,6 +1374,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
 #endif
     offs.push_back(heads_on_tc(ctx->nout) ? pack_dwpwtc_head<CfgNeckS2Tc>(P, f, "conv5_5", "conv5_6", "head_5", 128, ctx->nout)
                                           : pack_irb<CfgNeckS2>(P, f, "", "conv5_5", "conv5_6", "head_5", ctx->nout));
+    if (ctx->variant != YF_VARIANT_LITE) {
     offs.push_back(upcat_on_tc(ctx->H, ctx->W) ? pack_upcat_tc(P, f) : pack_upcat(P, f));
 #if YF_USE_TC
     offs.push_back(pack_dwpwtc<CfgNeckL1Tc>(P, f, "conv4_1_2", "conv4_1_3"));
@@ -1330,6 +1383,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
 #endif
     offs.push_back(heads_on_tc(ctx->nout) ? pack_dwpwtc_head<CfgNeckL2Tc>(P, f, "conv4_1_4", "conv4_1_5", "head_4", 96, ctx->nout)
                                           : pack_irb<CfgNeckL2>(P, f, "", "conv4_1_4", "conv4_1_5", "head_4", ctx->nout));
+    }
     pad4(P);
     if (offs.size() != ctx->groups.size()) { set_err(&ctx->err, "internal: %zu packs vs %zu groups", offs.size(), ctx->groups.size()); return YF_ERR_STATE; }
     for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.first);      // graphs bake the weight pointers in
@@ -1350,7 +1404,7 @@ static const int kForkMaxBatch = 128;   // measured: -9% at batch 1, -2% at 64, 
 static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* head_large, float* head_small, cudaStream_t st) {
     if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
     if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
-    if (!x || !head_large || !head_small) { set_err(&ctx->err, "null tensor pointer"); return YF_ERR_ARG; }
+    if (!x || !head_small || (!head_large && ctx->variant != YF_VARIANT_LITE)) { set_err(&ctx->err, "null tensor pointer"); return YF_ERR_ARG; }
     static const bool debug_sync = getenv("YF_DEBUG_SYNC") != nullptr;
     // Small batches leave most SMs idle in the low-resolution groups, so the two head branches (yolo_fastest.py:203-216: conv5_3..head_5
     // and deconv5_1..head_4, both fed by conv5_2) run side by side: fork after conv5_2, join before the caller's next work. Large
@@ -1391,8 +1445,19 @@ static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* hea
     return YF_OK;
 }
 
+// The asynchronous slot path (yf_detect_submit_u8*) runs on internal streams and shares the activations and the post-processing
+// workspace with the blocking entry points, which run on the caller's stream: every blocking entry point first makes its stream wait
+// for the slots in flight (a device-side dependency, no host block), so the two never overlap on those buffers.
+static int order_after_slots(yf_ctx* ctx, cudaStream_t st) {
+    for (int i = 0; i < 2; ++i)
+        if (ctx->sl_used[i]) CU(cudaStreamWaitEvent(st, ctx->sl_done[i], 0));
+    return YF_OK;
+}
+#define ORDER(ctx, st) do { int rc__ = order_after_slots(ctx, (cudaStream_t)(st)); if (rc__) return rc__; } while (0)
+
 extern "C" int yf_forward(yf_ctx* ctx, const float* x, int B, float* head_large, float* head_small, void* stream) {
     CTX_CHECK(ctx);
+    ORDER(ctx, stream);
     return forward_impl(ctx, x, false, B, head_large, head_small, (cudaStream_t)stream);
 }
 
@@ -1412,6 +1477,7 @@ extern "C" int yf_profile_forward(yf_ctx* ctx, const float* x, int B, const char
     CTX_CHECK(ctx);
     if (!ctx->weights_loaded) { set_err(&ctx->err, "weights not loaded"); return YF_ERR_STATE; }
     if (B < 1 || B > ctx->max_batch || !x) { set_err(&ctx->err, "bad arguments"); return YF_ERR_ARG; }
+    ORDER(ctx, 0);
     const int n = (int)ctx->groups.size();
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CU(cudaEventCreate(&e));
@@ -1478,12 +1544,14 @@ static int post_impl(yf_ctx* ctx, const float* hl, const float* hs, int B, int h
 extern "C" int yf_postprocess(yf_ctx* ctx, const float* head_large, const float* head_small, int B, int hl, int wl, int hs, int ws,
                               const yf_post_params* p, yf_det* out, int32_t* counts, int32_t* status, void* stream) {
     CTX_CHECK(ctx);
+    ORDER(ctx, stream);
     return post_impl(ctx, head_large, head_small, B, hl, wl, hs, ws, p, out, counts, status, 1, (cudaStream_t)stream);
 }
 
 extern "C" int yf_decode(yf_ctx* ctx, const float* head_large, const float* head_small, int B, int hl, int wl, int hs, int ws,
                          const yf_post_params* p, yf_det* out, int32_t* counts, int32_t* status, void* stream) {
     CTX_CHECK(ctx);
+    ORDER(ctx, stream);
     return post_impl(ctx, head_large, head_small, B, hl, wl, hs, ws, p, out, counts, status, 0, (cudaStream_t)stream);
 }
 
@@ -1511,6 +1579,7 @@ extern "C" int yf_val_nms(yf_ctx* ctx, const float* pred, int B, int N, double c
     if (!pred || !out || !counts || max_det < 1) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
     if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
     if (N < 1 || N > ctx->NC) { set_err(&ctx->err, "%d rows exceed the ctx capacity %d", N, ctx->NC); return YF_ERR_STATE; }
+    ORDER(ctx, stream);
     PostArgs a;
     memset(&a, 0, sizeof a);
     a.pred = pred;
@@ -1570,6 +1639,7 @@ static int detect_impl(yf_ctx* ctx, const void* x, bool u8in, int B, const yf_po
 extern "C" int yf_detect(yf_ctx* ctx, const float* x, int B, const yf_post_params* p, yf_det* out, int32_t* counts,
                          int32_t* status, void* stream) {
     CTX_CHECK(ctx);
+    ORDER(ctx, stream);
     return detect_impl(ctx, x, false, B, p, out, counts, status, (cudaStream_t)stream);
 }
 
@@ -1613,6 +1683,8 @@ static int detect_host_impl(yf_ctx* ctx, const void* x_host, bool u8in, int B, c
     if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
     if (p->max_det < 1) { set_err(&ctx->err, "max_det must be >= 1"); return YF_ERR_ARG; }
     CU(cudaSetDevice(ctx->device));
+    if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
+    ORDER(ctx, st);
     int rc = ensure_out(ctx, p->max_det);
     if (rc) return rc;
     const size_t npx = (size_t)B * ctx->in_ch * ctx->H * ctx->W;
@@ -1686,6 +1758,8 @@ extern "C" int yf_detect_host_bgr(yf_ctx* ctx, const uint8_t* bgr_host, int B, i
     if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
     if (p->max_det < 1) { set_err(&ctx->err, "max_det must be >= 1"); return YF_ERR_ARG; }
     CU(cudaSetDevice(ctx->device));
+    if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
+    ORDER(ctx, st);
     int rc = ensure_out(ctx, p->max_det);
     if (rc) return rc;
     const size_t nbytes = (size_t)B * Ho * Wo * 3;
@@ -1746,6 +1820,7 @@ static int submit_impl(yf_ctx* ctx, int slot, const uint8_t* u8_host, int B, con
     if (slot < 0 || slot > 1 || !u8_host || !p || !out_host || !counts_host) { set_err(&ctx->err, "bad argument"); return YF_ERR_ARG; }
     if (B < 1 || B > ctx->max_batch) { set_err(&ctx->err, "batch %d outside [1, max_batch=%d]", B, ctx->max_batch); return YF_ERR_STATE; }
     if (p->max_det < 1) { set_err(&ctx->err, "max_det must be >= 1"); return YF_ERR_ARG; }
+    if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
     CU(cudaSetDevice(ctx->device));
     int rc = slots_init(ctx);
     if (rc) return rc;

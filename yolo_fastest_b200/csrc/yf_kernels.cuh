@@ -1191,6 +1191,71 @@ upcat_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two chained 1x1 convs: relu(W1 x + b1) -> W2 . + b2 (linear). YoloFastest_lite's forward goes conv3_2 -> conv3_4 directly (it skips
+// the depthwise conv3_3, yolo_fastest.py:335-337), so that group has no spatial stage at all: one thread = 4 consecutive pixels, the
+// K inputs and N accumulators live in registers, the mid channels are produced and consumed one at a time; weights in smem.
+// Packed weights: [W1: K x M (k-major)][b1: M][W2: M x N (m-major)][b2: N]
+// ---------------------------------------------------------------------------------------------
+template <int K_, int M_, int N_, int NT_>
+struct PwPwCfg {
+    static constexpr int K = K_, M = M_, N = N_, NT = NT_;
+    static constexpr int OFF_W1 = 0, OFF_B1 = K * M, OFF_W2 = OFF_B1 + M, OFF_B2 = OFF_W2 + M * N;
+    static constexpr int WFLOATS = rup(OFF_B2 + N, 4);
+    static_assert(N % 4 == 0 && M % 2 == 0, "tiling");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT)
+pwpw_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts, int HW, long long total_groups) {
+    __shared__ __align__(16) float Ws[C::WFLOATS];
+    for (int i = threadIdx.x; i < C::WFLOATS; i += C::NT) Ws[i] = __ldg(wts + i);
+    __syncthreads();
+    const int gpi = HW / 4;                                    // pixel groups per image (HW % 4 == 0)
+    for (long long gidx = (long long)blockIdx.x * C::NT + threadIdx.x; gidx < total_groups; gidx += (long long)gridDim.x * C::NT) {
+        const int b = (int)(gidx / gpi);
+        const int p0 = (int)(gidx - (long long)b * gpi) * 4;
+        const float* xb = x + (size_t)b * C::K * HW + p0;
+        float xv[C::K][4];
+#pragma unroll
+        for (int k = 0; k < C::K; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)k * HW));
+            xv[k][0] = v.x; xv[k][1] = v.y; xv[k][2] = v.z; xv[k][3] = v.w;
+        }
+        float acc[C::N][4];
+#pragma unroll
+        for (int n = 0; n < C::N; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[n][i] = Ws[C::OFF_B2 + n];
+#pragma unroll 2
+        for (int m = 0; m < C::M; ++m) {
+            float e[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = Ws[C::OFF_B1 + m];
+#pragma unroll
+            for (int k = 0; k < C::K; ++k) {
+                const float w = Ws[C::OFF_W1 + k * C::M + m];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) e[i] = fmaf(w, xv[k][i], e[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = fmaxf(e[i], 0.f);
+#pragma unroll
+            for (int n4 = 0; n4 < C::N / 4; ++n4) {
+                const float4 w = ld4(Ws + C::OFF_W2 + m * C::N + 4 * n4);
+                const float w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 4; q += 2)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ffma2(w4[q], w4[q + 1], e[i], acc[4 * n4 + q][i], acc[4 * n4 + q + 1][i]);
+            }
+        }
+        float* yb = y + (size_t)b * C::N * HW + p0;
+#pragma unroll
+        for (int n = 0; n < C::N; ++n) st4(yb + (size_t)n * HW, make_float4(acc[n][0], acc[n][1], acc[n][2], acc[n][3]));
+    }
+}
+
 // u8 -> (x - 128) / 255 fp32 (detect.py:123-124) for callers that want the normalised tensor itself.
 __global__ void u8_normalize_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

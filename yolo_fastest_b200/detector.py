@@ -62,7 +62,12 @@ class YOLO_post_process:
             t = t.cuda()
         return t.contiguous().float()
 
-    def _run(self, pred, nms, mode=_lib.MODE_DETECT, max_det=None):
+    DEFAULT_CAP = 256     # result slots per image of the first attempt; the call is repeated with the exact size when an image has more
+
+    def _run(self, pred, nms, mode=_lib.MODE_DETECT, max_det=None, check_status=True):
+        """-> (per-image structured arrays, true counts, status). The reference has no cap on the list length (detect.py:155-169);
+        `max_det=None` reproduces that: a first pass with DEFAULT_CAP slots per image, repeated with the largest true count when
+        some image holds more. An explicit `max_det` is a hard capacity: an image with more detections raises instead of being cut."""
         hl, hs = self._to_cuda(pred[0]), self._to_cuda(pred[1])
         B = hl.shape[0]
         if hl.shape[1] != self.num_anchors * self.bbox_attrs or hs.shape[1] != hl.shape[1] or hs.shape[0] != B:
@@ -70,20 +75,30 @@ class YOLO_post_process:
                                % (tuple(hl.shape), tuple(hs.shape), self.num_anchors, self.bbox_attrs))
         ctx = self._context(hl.device, B)
         ncand = self.num_anchors * (hl.shape[2] * hl.shape[3] + hs.shape[2] * hs.shape[3])
-        max_det = ncand if max_det is None else max_det
-        out = torch.empty((B, max_det, _lib.DET_DTYPE.itemsize), dtype=torch.uint8, device=hl.device)
-        counts = torch.empty((B,), dtype=torch.int32, device=hl.device)
-        status = torch.empty((B,), dtype=torch.int32, device=hl.device)
-        p = self._params(mode, max_det)
+        cap = min(ncand, self.DEFAULT_CAP) if max_det is None else max_det
         fn = _lib.lib().yf_postprocess if nms else _lib.lib().yf_decode
         stream = torch.cuda.current_stream(hl.device).cuda_stream
-        with torch.cuda.device(hl.device):
-            _lib.check(fn(ctx.handle, hl.data_ptr(), hs.data_ptr(), B, hl.shape[2], hl.shape[3], hs.shape[2], hs.shape[3],
-                          C.byref(p), out.data_ptr(), counts.data_ptr(), status.data_ptr(), C.c_void_p(stream)), ctx.handle)
-        counts_h = counts.cpu().numpy()
-        status_h = status.cpu().numpy()
-        dets = out.cpu().numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
-        return [dets[b, :min(int(counts_h[b]), max_det)] for b in range(B)], counts_h, status_h
+        while True:
+            out = torch.empty((B, cap, _lib.DET_DTYPE.itemsize), dtype=torch.uint8, device=hl.device)
+            counts = torch.empty((B,), dtype=torch.int32, device=hl.device)
+            status = torch.empty((B,), dtype=torch.int32, device=hl.device)
+            p = self._params(mode, cap)
+            with torch.cuda.device(hl.device):
+                _lib.check(fn(ctx.handle, hl.data_ptr(), hs.data_ptr(), B, hl.shape[2], hl.shape[3], hs.shape[2], hs.shape[3],
+                              C.byref(p), out.data_ptr(), counts.data_ptr(), status.data_ptr(), C.c_void_p(stream)), ctx.handle)
+            counts_h = counts.cpu().numpy()
+            status_h = status.cpu().numpy()
+            if check_status and (status_h & 1).any():      # decode and decode + NMS alike
+                raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
+            most = int(counts_h.max()) if B else 0
+            if most <= cap:
+                break
+            if max_det is not None:
+                raise _lib.YfError("an image holds %d detections, more than max_det=%d: nothing is cut silently, pass a larger max_det" % (most, max_det))
+            cap = most
+        kmax = max(most, 1)
+        dets = out[:, :kmax].contiguous().cpu().numpy().view(_lib.DET_DTYPE).reshape(B, kmax)      # only the filled part travels
+        return [dets[b, :int(counts_h[b])] for b in range(B)], counts_h, status_h
 
     # ---- reference API (detect.py:41-84) --------------------------------------------------------
     def decode_box(self, pred):
@@ -119,24 +134,48 @@ class YOLO_post_process:
         """decode -> class split -> stable sort -> per-class NMS for every image (detect.py:155-169).
         Returns one list of rows per image (or the structured arrays with ``raw=True``)."""
         dets, counts, status = self._run(pred, nms=True, max_det=max_det)
-        if (status & 1).any():
-            raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
         return dets if raw else [_rows_from_dets(d) for d in dets]
 
 
 def plot_one_box(xyxy, img, color=None, label=None, line_thickness=None):
-    """Draw one labelled box (same look as the reference helper, utils/general.py:56-67). Host-side, cv2."""
+    """Box with an optional filled caption above its top-left corner, drawn into `img` (host-side, cv2). Call-compatible with the
+    helper the reference driver uses (utils/general.py:56-67: same arguments, line width scaled with the image, anti-aliased)."""
     import cv2
-    tl = line_thickness or round(0.002 * (img.shape[0] + img.shape[1]) / 2) + 1
-    color = color or [int(v) for v in np.random.randint(0, 255, 3)]
-    c1, c2 = (int(xyxy[0]), int(xyxy[1])), (int(xyxy[2]), int(xyxy[3]))
-    cv2.rectangle(img, c1, c2, color, thickness=tl, lineType=cv2.LINE_AA)
-    if label:
-        tf = min(tl - 1, 2)
-        t_size = cv2.getTextSize(label, fontFace=0, fontScale=tl / 5, thickness=tf)[0]
-        c2 = c1[0] + t_size[0], c1[1] - t_size[1] - 3
-        cv2.rectangle(img, c1, c2, color, thickness=-1, lineType=cv2.LINE_AA)
-        cv2.putText(img, label, (c1[0], c1[1] - 2), 0, tl / 5, [225, 255, 255], thickness=tf, lineType=cv2.LINE_AA)
+    h, w = img.shape[:2]
+    width = int(line_thickness) if line_thickness else int(round(0.001 * (h + w))) + 1
+    if color is None:
+        color = np.random.randint(0, 255, 3).tolist()
+    left, top, right, bottom = (int(v) for v in xyxy[:4])
+    cv2.rectangle(img, (left, top), (right, bottom), color, width, cv2.LINE_AA)
+    if not label:
+        return
+    scale, stroke = width / 5.0, max(min(width - 1, 2), 1)
+    (tw, th), _ = cv2.getTextSize(label, cv2.FONT_HERSHEY_SIMPLEX, scale, stroke)
+    cv2.rectangle(img, (left, top), (left + tw, top - th - 3), color, -1, cv2.LINE_AA)          # caption background
+    cv2.putText(img, label, (left, top - 2), cv2.FONT_HERSHEY_SIMPLEX, scale, (225, 255, 255), stroke, cv2.LINE_AA)
+
+
+def _finish(pin_out, pin_cnt, pin_st, B, max_det, rerun):
+    """Host tail of every batched detect call: status check, and NO silent truncation (the reference's lists have no cap,
+    detect.py:155-169): when an image holds more than `max_det` detections the batch is run again with room for all of them."""
+    if (pin_st.numpy() & 1).any():
+        raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
+    counts = pin_cnt.numpy()
+    most = int(counts.max()) if B else 0
+    if most > max_det:
+        return rerun(most)
+    dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
+    return [dets[b, :int(counts[b])].copy() for b in range(B)]
+
+
+def _check_u8_host(t, input_shape, what):
+    """Shared validation of the asynchronous entry points: a contiguous host uint8 tensor [B, H, W] at the network input size."""
+    if not (isinstance(t, torch.Tensor) and t.dtype == torch.uint8 and t.is_contiguous() and not t.is_cuda and t.dim() == 3):
+        raise _lib.YfError("%s takes a contiguous host uint8 tensor [B, H, W] (pinned for asynchronous copies)" % what)
+    if list(t.shape[1:]) != list(input_shape[0:2]):
+        raise _lib.YfError("images are %dx%d, the network input is %s" % (t.shape[1], t.shape[2], input_shape[0:2]))
+    if input_shape[2] != 1:
+        raise _lib.YfError("%s serves the single-channel networks" % what)
 
 
 class Detect_YOLO:
@@ -237,11 +276,7 @@ class Detect_YOLO:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().yf_detect_host_bgr(ctx.handle, t.data_ptr(), B, Ho, Wo, C.byref(p), pin_out.data_ptr(),
                                                     pin_cnt.data_ptr(), pin_st.data_ptr(), C.c_void_p(stream)), ctx.handle)
-        if (pin_st.numpy() & 1).any():
-            raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
-        counts = pin_cnt.numpy()
-        dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
-        res = [dets[b, :min(int(counts[b]), max_det)].copy() for b in range(B)]
+        res = _finish(pin_out, pin_cnt, pin_st, B, max_det, lambda need: self.detect_bgr_batch(bgr, max_det=need, raw=True, adjust=False))
         if raw:
             return res
         rows = [_rows_from_dets(d) for d in res]
@@ -287,23 +322,15 @@ class Detect_YOLO:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().yf_detect_host_u8(ctx.handle, pin_in.data_ptr(), B, C.byref(p), pin_out.data_ptr(),
                                                    pin_cnt.data_ptr(), pin_st.data_ptr(), C.c_void_p(stream)), ctx.handle)
-        counts = pin_cnt.numpy()
-        if (pin_st.numpy() & 1).any():
-            raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
-        dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
-        res = [dets[b, :min(int(counts[b]), max_det)].copy() for b in range(B)]
+        res = _finish(pin_out, pin_cnt, pin_st, B, max_det, lambda need: self.detect_batch(u8_batch, max_det=need, raw=True))
         return res if raw else [_rows_from_dets(d) for d in res]
 
     def submit_batch(self, u8_pinned, slot, max_det=64):
         """Asynchronous form of detect_batch for serving loops (yf_detect_submit_u8): `u8_pinned` is a pinned host
         uint8 tensor [B, H, W] that must stay untouched until `collect(slot)`. Submitting the next batch into the
         other slot before collecting this one overlaps its host-to-device copy with this batch's compute."""
-        if not (isinstance(u8_pinned, torch.Tensor) and u8_pinned.dtype == torch.uint8 and u8_pinned.is_contiguous()
-                and not u8_pinned.is_cuda):
-            raise _lib.YfError("submit_batch takes a contiguous host uint8 tensor (pinned for asynchronous copies)")
+        _check_u8_host(u8_pinned, self.input_shape, "submit_batch")
         B, H, W = u8_pinned.shape
-        if [H, W] != list(self.input_shape[0:2]):
-            raise _lib.YfError("images are %dx%d, the network input is %s" % (H, W, self.input_shape[0:2]))
         ctx = self.model.context(self.device, H, W, B)
         st = self._slots.get(slot)
         if st is None or st[0] != (B, max_det):
@@ -317,10 +344,13 @@ class Detect_YOLO:
                                                      pin_cnt.data_ptr(), pin_st.data_ptr()), ctx.handle)
         self._slot_ref = getattr(self, "_slot_ref", {})
         self._slot_ref[slot] = u8_pinned          # keep the input alive until collected
+        ctx.pending.add(slot)
 
     def submit_batch_device(self, u8_pinned, slot, max_det=64):
         """As submit_batch, but the results stay on the device: returns (dets uint8 [B, max_det, 56], counts int32 [B])
-        cuda tensors that are complete once `wait(slot)` has returned (multi-GPU jobs gather them with NCCL)."""
+        cuda tensors that are complete once `wait(slot)` has returned (multi-GPU jobs gather them with NCCL). counts[b] may exceed
+        max_det: the slab then holds the first max_det records of image b in (class, conf) order — check it where that can happen."""
+        _check_u8_host(u8_pinned, self.input_shape, "submit_batch_device")
         B, H, W = u8_pinned.shape
         ctx = self.model.context(self.device, H, W, B)
         key = ("dev", slot)
@@ -336,24 +366,23 @@ class Detect_YOLO:
                                                          cnt.data_ptr(), None), ctx.handle)
         self._slot_ref = getattr(self, "_slot_ref", {})
         self._slot_ref[slot] = u8_pinned
+        ctx.pending.add(slot)
         return out, cnt
 
     def wait(self, slot):
         ctx = self.model._ctx
         _lib.check(_lib.lib().yf_detect_wait(ctx.handle, slot), ctx.handle)
         self._slot_ref.pop(slot, None)
+        ctx.pending.discard(slot)
 
     def collect(self, slot, raw=False):
         """Wait for the batch submitted into `slot` and return its per-image detections."""
         ctx = self.model._ctx
         (B, max_det), pin_out, pin_cnt, pin_st = self._slots[slot]
         _lib.check(_lib.lib().yf_detect_wait(ctx.handle, slot), ctx.handle)
-        self._slot_ref.pop(slot, None)
-        if (pin_st.numpy() & 1).any():
-            raise _lib.YfError("decoded box coordinates beyond 2^25: outside the exact-arithmetic domain of the GPU path")
-        counts = pin_cnt.numpy()
-        dets = pin_out.numpy().view(_lib.DET_DTYPE).reshape(B, max_det)
-        res = [dets[b, :min(int(counts[b]), max_det)].copy() for b in range(B)]
+        src = self._slot_ref.pop(slot, None)
+        ctx.pending.discard(slot)
+        res = _finish(pin_out, pin_cnt, pin_st, B, max_det, lambda need: self.detect_batch(src, max_det=need, raw=True))
         return res if raw else [_rows_from_dets(d) for d in res]
 
     def detect_device(self, x, max_det=64):

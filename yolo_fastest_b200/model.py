@@ -96,22 +96,26 @@ class BasicResBlock(nn.Module):
 
 
 def _fold(conv_w, bn, transposed=False):
-    """Eval-mode BN folded into the conv in fp64: w' = w*g/sqrt(v+eps), b' = beta - mean*g/sqrt(v+eps)."""
-    w = conv_w.detach().double().cpu()
-    g, b = bn.weight.detach().double().cpu(), bn.bias.detach().double().cpu()
-    m, v = bn.running_mean.detach().double().cpu(), bn.running_var.detach().double().cpu()
+    """Eval-mode BN folded into the conv in fp64: w' = w*g/sqrt(v+eps), b' = beta - mean*g/sqrt(v+eps). The parameters live on the
+    host (YoloFastest.to / .cuda do not move them), so nothing here touches the device."""
+    w = conv_w.detach().double()
+    g, b = bn.weight.detach().double(), bn.bias.detach().double()
+    m, v = bn.running_mean.detach().double(), bn.running_var.detach().double()
     s = g / torch.sqrt(v + bn.eps)
     w = w * (s.view(1, -1, 1, 1) if transposed else s.view(-1, 1, 1, 1))
     return w.float().numpy().ravel(), (b - m * s).float().numpy().ravel()
 
 
 class YoloFastest(nn.Module):
+    VARIANT = _lib.VARIANT_FULL
+
     def __init__(self, io_params):
         super().__init__()
         self.num_cls = io_params["num_cls"]
         self.input_channel = io_params["input_channel"]
         self.num_anchors = io_params["num_anchors"]
-        self.num_out = self.num_anchors * (5 + self.num_cls)
+        # yolo_fastest.py:74-75; the lite class multiplies its anchor count by the class count first (:240-241)
+        self.num_out = (self.num_anchors * self.num_cls if self.VARIANT == _lib.VARIANT_LITE else self.num_anchors) * (5 + self.num_cls)
         for name, kind, cin, cout, k, s, dw, relu in ARCH:
             if kind == "cbr":
                 mod = _cbr(self.input_channel if cin is None else cin, cout, k, s, dw, relu)
@@ -152,6 +156,18 @@ class YoloFastest(nn.Module):
         self._dirty = True
         return out
 
+    # The 508 state_dict tensors are STORAGE for the host-side fold; the device only ever sees the packed blob (yf_load_weights).
+    # `.to(device)` / `.cuda()` therefore keep them on the host (detect.py:89 calls `.to(device)`; moving 508 small tensors to the GPU
+    # and pulling each back to fold it cost hundreds of tiny copies and syncs per context). dtype conversions still apply.
+    def to(self, *args, **kwargs):
+        device, dtype, _, _ = torch._C._nn._parse_to(*args, **kwargs)
+        if dtype is not None:
+            super().to(dtype=dtype)
+        return self
+
+    def cuda(self, device=None):
+        return self
+
     def refresh(self):
         """Call after mutating parameters in place; the next forward re-folds and re-uploads them."""
         self._dirty = True
@@ -172,7 +188,7 @@ class YoloFastest(nn.Module):
             else:
                 parts.extend(_fold(mod[0].weight, mod[1], transposed=True))
         blob = np.concatenate(parts).astype(np.float32)
-        expect = _lib.lib().yf_weight_count(self.input_channel, self.num_cls, self.num_anchors)
+        expect = _lib.lib().yf_weight_count_variant(self.input_channel, self.num_cls, self.num_anchors, self.VARIANT)
         if blob.size != expect:
             raise _lib.YfError("folded blob has %d floats, library expects %d" % (blob.size, expect))
         return blob
@@ -228,10 +244,12 @@ class YoloFastest(nn.Module):
         c = self._ctx
         if c is None or c.device_index != idx or c.H != H or c.W != W or c.max_batch < batch:
             if c is not None:
+                if c.pending:
+                    raise _lib.YfError("a larger batch needs a new context, but slots %s hold submitted batches: collect them first" % sorted(c.pending))
                 torch.cuda.synchronize(c.device_index)
                 c.close()
             with torch.cuda.device(idx):
-                c = _lib.Ctx(idx, self.input_channel, self.num_cls, self.num_anchors, batch, H, W)
+                c = _lib.Ctx(idx, self.input_channel, self.num_cls, self.num_anchors, batch, H, W, self.VARIANT)
             self._ctx = c
             self._dirty = True
         if self._dirty:
@@ -290,3 +308,39 @@ class YoloFastest(nn.Module):
         if n < 0:
             _lib.check(n, ctx.handle)
         return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+
+class YoloFastest_lite(YoloFastest):
+    """Drop-in for the reference's single-head variant (yolo_fastest.py:234-387): the same parameter set and state_dict keys as
+    YoloFastest with (num_anchors * num_cls) * (5 + num_cls) head channels (:240-241); its forward goes conv3_2 -> conv3_4 without the
+    depthwise conv3_3 (:335-337), ends at head_5 and returns that single tensor (:365-372). Same kernels, one more launch plan
+    (YF_VARIANT_LITE); the reference's `initialize_weights` additionally sets BatchNorm eps 1e-3 / momentum 0.03 (:383-385)."""
+    VARIANT = _lib.VARIANT_LITE
+
+    def initialize_weights(self):
+        super().initialize_weights()
+        for m in self.modules():
+            if type(m) is nn.BatchNorm2d:
+                m.eps = 1e-3
+                m.momentum = 0.03
+        self._dirty = True
+
+    def load_state_dict(self, *args, **kwargs):
+        eps = {k: m.eps for k, m in self.named_modules() if isinstance(m, nn.BatchNorm2d)}
+        out = super().load_state_dict(*args, **kwargs)
+        for k, m in self.named_modules():              # a checkpoint does not carry eps: keep what the instance had
+            if isinstance(m, nn.BatchNorm2d):
+                m.eps = eps[k]
+        return out
+
+    def forward(self, x):
+        """[B, 1, H, W] fp32 cuda -> head_5 [B, A*nc*(5+nc), H/32, W/32]."""
+        self._check_input(x)
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        ctx = self.context(x.device, H, W, B)
+        head = torch.empty((B, self.num_out, H // 32, W // 32), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().yf_forward(ctx.handle, x.data_ptr(), B, None, head.data_ptr(), C.c_void_p(stream)), ctx.handle)
+        return head

@@ -28,9 +28,12 @@ def _context(device, num_cls, num_anchors, batch, ncand):
         # candidate capacity of a ctx is A*(H/16*W/16 + H/32*W/32) = A*5*(H/32)*(W/32): size a square-ish dummy input to hold ncand
         cells = -(-ncand // (5 * num_anchors))
         side = int(np.ceil(np.sqrt(cells)))
-        with torch.cuda.device(idx):
+        with torch.cuda.device(idx):       # post-only: a ctx allocates its forward buffers with its first weights, i.e. never here
             c = _lib.Ctx(idx, 1, num_cls, num_anchors, max(batch, 1), 32 * side, 32 * side)
         _ctx_cache[key] = c
+        while len(_ctx_cache) > 4:         # a handful of (device, classes, anchors) combinations at most stay alive
+            old_key = next(k for k in _ctx_cache if k != key)
+            _ctx_cache.pop(old_key).close()
     return c
 
 
@@ -75,15 +78,22 @@ def non_max_suppression(prediction, num_classes, conf_thres=0.5, nms_thres=0.4, 
     if attrs != 5 + num_classes:
         raise _lib.YfError("rows have %d columns, expected %d" % (attrs, 5 + num_classes))
     ctx = _context(pred.device, num_classes, num_anchors, B, N)
-    out = torch.empty((B, N, _lib.DET_DTYPE.itemsize), dtype=torch.uint8, device=pred.device)
-    counts = torch.empty((B,), dtype=torch.int32, device=pred.device)
-    status = torch.empty((B,), dtype=torch.int32, device=pred.device)
     stream = torch.cuda.current_stream(pred.device).cuda_stream
-    with torch.cuda.device(pred.device):
-        _lib.check(_lib.lib().yf_val_nms(ctx.handle, pred.data_ptr(), B, N, float(conf_thres), float(nms_thres), N,
-                                        out.data_ptr(), counts.data_ptr(), status.data_ptr(), C.c_void_p(stream)), ctx.handle)
-    counts_h = counts.cpu().numpy()
-    dets = out.cpu().numpy().view(_lib.DET_DTYPE).reshape(B, N)
+    cap = min(N, 256)            # the reference's lists have no cap (general.py:87-143): repeat with the exact size when an image holds more
+    while True:
+        out = torch.empty((B, cap, _lib.DET_DTYPE.itemsize), dtype=torch.uint8, device=pred.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=pred.device)
+        status = torch.empty((B,), dtype=torch.int32, device=pred.device)
+        with torch.cuda.device(pred.device):
+            _lib.check(_lib.lib().yf_val_nms(ctx.handle, pred.data_ptr(), B, N, float(conf_thres), float(nms_thres), cap,
+                                            out.data_ptr(), counts.data_ptr(), status.data_ptr(), C.c_void_p(stream)), ctx.handle)
+        counts_h = counts.cpu().numpy()
+        most = int(counts_h.max()) if B else 0
+        if most <= cap:
+            break
+        cap = most
+    kmax = max(most, 1)
+    dets = out[:, :kmax].contiguous().cpu().numpy().view(_lib.DET_DTYPE).reshape(B, kmax)      # only the filled part travels
     result = []
     for b in range(B):
         d = dets[b, :int(counts_h[b])]
