@@ -187,6 +187,18 @@ def test_ncnn_weight_source(gold):
         assert float((got_h - ref_h).abs().max()) <= 1e-4 * float(ref_h.abs().max())
 
 
+def test_onnx_weight_source(gold):
+    """Weights taken from the reference's ONNX export (YoloFastest.load_onnx) give the shipped checkpoint's detections."""
+    res = "256x320"
+    g = gold.res[res]
+    det = yf.Detect_YOLO(torch.device("cuda:0"), gold.ckpt("yolo_fastest_" + res), yf.config_for(res), None)
+    det.model.load_state_dict({k: torch.zeros_like(v) for k, v in det.model.state_dict().items()})       # nothing of the .pth survives
+    det.model.load_onnx(os.path.join(GOLD, "onnx", "YOLO-Fastest_epoch_28.onnx"))
+    rows = det.detect_batch(g["u8"], max_det=16)
+    for i in range(len(g["u8"])):
+        _match([list(r) for r in g["kept_%02d" % i]], rows[i])
+
+
 def test_three_channel_detect_u8_equals_float(gold, tmp_path):
     """3-channel network through Detect_YOLO: uint8 RGB planes [B, 3, H, W] with the normalisation fused into the stem give the
     detections of the normalised fp32 batch, and those of the oracle."""

@@ -237,6 +237,49 @@ class YoloFastest(nn.Module):
         self._dirty = True
         return self
 
+    def _slots(self):
+        """(conv module, bn module or None, transposed) per convolution, in forward order"""
+        slots = []
+        for name, kind, *_ in ARCH:
+            mod = getattr(self, name)
+            if kind == "cbr":
+                slots.append((mod[0], mod[1], False))
+            elif kind == "res":
+                slots.extend((sub[0], sub[1], False) for sub in (mod.conv1, mod.conv2, mod.conv3))
+            elif kind == "head":
+                slots.append((mod, None, False))
+            else:
+                slots.append((mod[0], mod[1], True))
+        return slots
+
+    def load_onnx(self, path):
+        """Take the parameters from the reference's ONNX export (`models/onnx/<res>/*.onnx`): convolution kernels,
+        BatchNorm scale / bias / mean / var / epsilon and the head biases go into the module's own tensors, so `folded_blob` folds them
+        exactly as it folds a `.pth`. The node table is checked against the architecture first."""
+        from . import onnx_loader
+        layers = onnx_loader.read_onnx(path)
+        slots = self._slots()
+        if len(layers) != len(slots):
+            raise _lib.YfError("ONNX file has %d convolutions, YOLO-Fastest has %d" % (len(layers), len(slots)))
+        with torch.no_grad():
+            for (conv, bn, transposed), l in zip(slots, layers):
+                w = torch.from_numpy(l["weight"])
+                if tuple(w.shape) != tuple(conv.weight.shape) or transposed != (l["type"] == "ConvTranspose") or (bn is None) != (l["bn"] is None) \
+                        or l["group"] != conv.groups or l["stride"] != conv.stride[0]:
+                    raise _lib.YfError("ONNX node %s (%s %s, stride %d, group %d) does not match %s"
+                                       % (l["name"], l["type"], tuple(w.shape), l["stride"], l["group"], tuple(conv.weight.shape)))
+                conv.weight.copy_(w)
+                if bn is None:
+                    conv.bias.copy_(torch.from_numpy(l["bias"]))
+                else:
+                    bn.weight.copy_(torch.from_numpy(l["bn"]["scale"]))
+                    bn.bias.copy_(torch.from_numpy(l["bn"]["bias"]))
+                    bn.running_mean.copy_(torch.from_numpy(l["bn"]["mean"]))
+                    bn.running_var.copy_(torch.from_numpy(l["bn"]["var"]))
+                    bn.eps = l["bn"]["eps"]
+        self._dirty = True
+        return self
+
     # ---- execution ---------------------------------------------------------------------------
     def context(self, device, H, W, batch):
         """The yf_ctx serving (device, H, W); grown (re-created) when a larger batch arrives."""
