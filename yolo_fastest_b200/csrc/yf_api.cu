@@ -1271,6 +1271,9 @@ extern "C" int yf_create_variant(yf_ctx** out, int device, int in_ch, int num_cl
         cudaFuncSetAttribute(upcat_tc_kernel<CfgUpCatTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCatTc::SMEM_BYTES),
         init_irb<CfgRes1>(),
         init_wirb<CfgRes1W>(), init_wirb<CfgRes2W>(), init_wirb<CfgDown2W>(), init_wstem<CfgStemW>(),
+        cudaFuncSetAttribute(post_kernel<YF_MODE_DETECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
+        cudaFuncSetAttribute(post_kernel<YF_MODE_VALIDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
+        cudaFuncSetAttribute(post_kernel<POST_SRC_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
         init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
@@ -1515,6 +1518,14 @@ extern "C" int yf_debug_trace(long long* dst, int n) {
 // ---------------------------------------------------------------------------------------------
 // post-processing
 // ---------------------------------------------------------------------------------------------
+// shared-memory sort capacity of the head kernel for NC candidates: the next power of two, 12 bytes per key; beyond 16 384 keys
+// (196 KB) the kernel falls back to its global-memory rank
+static int post_sort_cap(int NC) {
+    int p2 = 32;
+    while (p2 < NC) p2 <<= 1;
+    return p2 <= 16384 ? p2 : 0;
+}
+
 static int post_impl(yf_ctx* ctx, const float* hl, const float* hs, int B, int hlh, int hlw, int hsh, int hsw,
                      const yf_post_params* p, yf_det* out, int32_t* counts, int32_t* status, int do_nms, cudaStream_t st) {
     if (!p || !hl || !hs || !out || !counts) { set_err(&ctx->err, "null argument"); return YF_ERR_ARG; }
@@ -1534,8 +1545,9 @@ static int post_impl(yf_ctx* ctx, const float* hl, const float* hs, int B, int h
     a.out = out; a.counts = counts; a.status = status;
     a.NC = NC;
     a.rec = ctx->p_rec; a.conf = ctx->p_conf; a.cls = ctx->p_cls; a.sbox = ctx->p_sbox; a.order = ctx->p_order; a.alive = ctx->p_alive;
-    if (p->mode == YF_MODE_DETECT) post_kernel<YF_MODE_DETECT><<<B, POST_NT, 0, st>>>(a);
-    else post_kernel<YF_MODE_VALIDATE><<<B, POST_NT, 0, st>>>(a);
+    a.sort_cap = post_sort_cap(NC);
+    if (p->mode == YF_MODE_DETECT) post_kernel<YF_MODE_DETECT><<<B, POST_NT, a.sort_cap * 12, st>>>(a);
+    else post_kernel<YF_MODE_VALIDATE><<<B, POST_NT, a.sort_cap * 12, st>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return YF_OK;
@@ -1589,7 +1601,8 @@ extern "C" int yf_val_nms(yf_ctx* ctx, const float* pred, int B, int N, double c
     a.out = out; a.counts = counts; a.status = status;
     a.NC = N;
     a.rec = ctx->p_rec; a.conf = ctx->p_conf; a.cls = ctx->p_cls; a.sbox = ctx->p_sbox; a.order = ctx->p_order; a.alive = ctx->p_alive;
-    post_kernel<POST_SRC_ROWS><<<B, POST_NT, 0, (cudaStream_t)stream>>>(a);
+    a.sort_cap = post_sort_cap(N);
+    post_kernel<POST_SRC_ROWS><<<B, POST_NT, a.sort_cap * 12, (cudaStream_t)stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return YF_OK;

@@ -1,5 +1,15 @@
 // yf_post.cuh — the head kernel: decode of both YOLO scales, confidence filter, warp-ballot
-// ordered compaction, stable per-class sort and greedy per-class NMS, one CTA per image.
+// ordered compaction, stable per-class sort and greedy per-class NMS, one CTA (512 threads) per image.
+//
+//   sort   the survivors' keys (class asc, conf desc, candidate index asc — Python's stable list.sort per class, detect.py:157-167)
+//          live in SHARED memory as (float64 conf, class << 21 | slot) pairs and are ordered by one bitonic network over the next
+//          power of two >= n: O(n log^2 n) compare-exchanges on chip instead of an O(n^2) rank over global memory.
+//   NMS    bitmask formulation: a chunk of 32 sorted boxes is a 32x32 IoU tile — every lane evaluates its box against the 32 boxes of
+//          the chunk (all IoUs in parallel, off the serial chain) and packs the results into one suppression word; the greedy
+//          resolution then walks the words (one shuffle + two logic ops per box). The chunk's kept boxes knock out the later boxes
+//          of the class. Classes of up to 64 boxes are resolved by one warp each, all warps in parallel (the 80-class stress
+//          configuration: 80 classes x ~32 boxes); larger classes are processed by the WHOLE CTA chunk by chunk — warp 0 resolves
+//          the tile, all 16 warps apply its kept boxes to the rest of the class.
 //
 //   YF_MODE_DETECT   src/detect.py:23-84,155-169   float64 sigmoid/exp on the fp32 logits,
 //                    Python round() (half-to-even) to integer boxes, strict '>' tests, IoU
@@ -18,7 +28,7 @@
 
 namespace yf {
 
-constexpr int POST_NT = 256;
+constexpr int POST_NT = 512;
 constexpr int POST_NW = POST_NT / 32;
 constexpr int POST_MAX_CLS = 2048;
 
@@ -42,6 +52,7 @@ struct PostArgs {
     int4* sbox;           // boxes in sorted order: int32 coords (detect) or fp32 bit patterns (validate)
     int32_t* order;       // sorted position -> survivor slot
     unsigned char* alive; // per sorted position
+    int sort_cap;         // elements the dynamic shared memory holds for the sort (a power of two; 0: fall back to the global rank)
 };
 
 // Ordered block compaction: every thread calls with its predicate; returns the slot of this
@@ -110,9 +121,30 @@ __device__ __forceinline__ int4 shfl4(const int4 v, int src) {
     return r;
 }
 
-// Greedy NMS of one conf-descending segment [st, en) by one warp (detect.py:69-84 / general.py:127-136).
-// Chunks of 32: lanes resolve the chunk against itself in order, then the chunk's kept boxes
-// knock out every later box of the segment. alive[] is read and written by the same lane only.
+// ---- bitmask NMS ---------------------------------------------------------------------------------------------------------------
+// One 32x32 tile: lane j holds box j of the chunk (`mine`, `in`/`al` = exists / still alive). Returns the chunk's kept mask and
+// updates `al`. Step 1: lane j evaluates suppress(i, j) for every earlier box i of the chunk -> word w_j (bit i). Step 2: greedy
+// walk over the words: box j is kept iff it is alive and no kept earlier box has its bit set in w_j.
+template <int MODE>
+__device__ __forceinline__ unsigned nms_tile(const int4 mine, bool& al, int cnt, double thres_d, float thres_f) {
+    const int lane = threadIdx.x & 31;
+    unsigned w = 0;
+    for (int i = 0; i < cnt; ++i) {
+        const int4 bi = shfl4(mine, i);
+        if (i < lane && suppress<MODE>(bi, mine, thres_d, thres_f)) w |= 1u << i;
+    }
+    const unsigned alive_in = __ballot_sync(0xffffffffu, al);
+    unsigned kept = 0;
+    for (int j = 0; j < cnt; ++j) {
+        const unsigned wj = __shfl_sync(0xffffffffu, w, j);
+        if (((alive_in >> j) & 1u) && (wj & kept) == 0u) kept |= 1u << j;
+    }
+    al = (kept >> lane) & 1u;
+    return kept;
+}
+
+// Greedy NMS of one conf-descending segment [st, en) by one warp (detect.py:69-84 / general.py:127-136): tiles of 32 in order;
+// the kept boxes of a tile knock out every later box of the segment. alive[] is read and written by the same lane only.
 template <int MODE>
 __device__ __forceinline__ void warp_nms_segment(const int4* __restrict__ sbox, unsigned char* __restrict__ alive,
                                                  int st, int en, double thres_d, float thres_f) {
@@ -122,14 +154,8 @@ __device__ __forceinline__ void warp_nms_segment(const int4* __restrict__ sbox, 
         const bool in = p < en;
         const int4 mine = in ? sbox[p] : make_int4(0, 0, 0, 0);
         bool al = in && alive[p];
-        const int cnt = min(32, en - s);
-        for (int i = 0; i < cnt; ++i) {
-            const bool ai = __shfl_sync(0xffffffffu, (int)al, i) != 0;
-            const int4 bi = shfl4(mine, i);
-            if (ai && al && lane > i && suppress<MODE>(bi, mine, thres_d, thres_f)) al = false;
-        }
+        const unsigned kept = nms_tile<MODE>(mine, al, min(32, en - s), thres_d, thres_f);
         if (in) alive[p] = al ? 1 : 0;
-        const unsigned kept = __ballot_sync(0xffffffffu, al);
         if (kept == 0u) continue;
         for (int qb = s + 32; qb < en; qb += 32) {
             const int q = qb + lane;
@@ -146,11 +172,55 @@ __device__ __forceinline__ void warp_nms_segment(const int4* __restrict__ sbox, 
     }
 }
 
+// The same for a LARGE segment by the whole CTA (every thread calls it with the same arguments): per tile warp 0 resolves the
+// 32x32 tile and publishes its kept boxes in shared memory, then all warps apply them to the later boxes of the segment.
+template <int MODE>
+__device__ __forceinline__ void block_nms_segment(const int4* __restrict__ sbox, unsigned char* __restrict__ alive,
+                                                  int st, int en, double thres_d, float thres_f, int4* s_kbox, int* s_nk) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int s = st; s < en; s += 32) {
+        if (wid == 0) {
+            const int p = s + lane;
+            const bool in = p < en;
+            const int4 mine = in ? sbox[p] : make_int4(0, 0, 0, 0);
+            bool al = in && alive[p];
+            const unsigned kept = nms_tile<MODE>(mine, al, min(32, en - s), thres_d, thres_f);
+            if (in) alive[p] = al ? 1 : 0;
+            if (al) s_kbox[__popc(kept & ((1u << lane) - 1u))] = mine;
+            if (lane == 0) *s_nk = __popc(kept);
+        }
+        __syncthreads();
+        const int nk = *s_nk;
+        if (nk > 0) {
+            for (int q = s + 32 + (int)threadIdx.x; q < en; q += POST_NT) {
+                if (!alive[q]) continue;
+                const int4 bq = sbox[q];
+                bool aq = true;
+                for (int i = 0; i < nk && aq; ++i)
+                    if (suppress<MODE>(s_kbox[i], bq, thres_d, thres_f)) aq = false;
+                if (!aq) alive[q] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// sort order of the survivors: class ascending, conf descending, slot (= candidate order) ascending; key2 = class << 21 | slot
+__device__ __forceinline__ bool key_before(double ca, uint32_t ka, double cb, uint32_t kb) {
+    const uint32_t cla = ka >> 21, clb = kb >> 21;
+    if (cla != clb) return cla < clb;
+    if (ca != cb) return ca > cb;
+    return ka < kb;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(POST_NT) post_kernel(const PostArgs a) {
+    extern __shared__ __align__(16) unsigned char post_smem[];       // sort keys: double conf[sort_cap], uint32 key2[sort_cap]
     __shared__ int s_wc[POST_NW];
     __shared__ int s_start[POST_MAX_CLS + 1];
     __shared__ int s_flags;
+    __shared__ int4 s_kbox[32];
+    __shared__ int s_nk;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int attrs = 5 + a.nc;
@@ -289,22 +359,50 @@ __global__ void __launch_bounds__(POST_NT) post_kernel(const PostArgs a) {
         return;
     }
 
-    // ---- phase 2: class offsets + stable rank inside the class ---------------------------------
+    // ---- phase 2: class offsets + stable sort inside the class -----------------------------------
     if (tid == 0) {
         int run = 0;
         for (int c = 0; c <= a.nc; ++c) { run += s_start[c]; s_start[c] = run; }   // s_start[c] = first slot of class c
     }
     __syncthreads();
-    // rank = #{t in same class : conf_t > conf_s, or equal and earlier} (stable descending sort, detect.py:167)
-    for (int s = tid; s < n; s += POST_NT) {
-        const int c = clss[s];
-        const double cf = confs[s];
-        int r = 0;
-        for (int t = 0; t < n; ++t) {
-            const double ct = confs[t];
-            r += (clss[t] == c) && (ct > cf || (ct == cf && t < s));
+    int np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    if (np2 <= a.sort_cap) {
+        // bitonic network over (class, -conf, slot) keys in shared memory; padding keys sort last (class field all ones)
+        double* kc = reinterpret_cast<double*>(post_smem);
+        uint32_t* kk = reinterpret_cast<uint32_t*>(kc + a.sort_cap);
+        for (int s = tid; s < np2; s += POST_NT) {
+            kc[s] = s < n ? confs[s] : 0.0;
+            kk[s] = s < n ? ((uint32_t)clss[s] << 21 | (uint32_t)s) : 0xFFFFFFFFu;
         }
-        order[s_start[c] + r] = s;
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < np2; i += POST_NT) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const double ci = kc[i], cl = kc[l];
+                        const uint32_t ki = kk[i], kl = kk[l];
+                        const bool up = (i & k) == 0;                    // ascending block: the earlier key goes to the lower index
+                        if (key_before(cl, kl, ci, ki) == up) { kc[i] = cl; kc[l] = ci; kk[i] = kl; kk[l] = ki; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int pos = tid; pos < n; pos += POST_NT) order[pos] = (int)(kk[pos] & 0x1FFFFFu);
+    } else {
+        // more survivors than the shared-memory sort holds: rank = #{t in same class : conf_t > conf_s, or equal and earlier}
+        for (int s = tid; s < n; s += POST_NT) {
+            const int c = clss[s];
+            const double cf = confs[s];
+            int r = 0;
+            for (int t = 0; t < n; ++t) {
+                const double ct = confs[t];
+                r += (clss[t] == c) && (ct > cf || (ct == cf && t < s));
+            }
+            order[s_start[c] + r] = s;
+        }
     }
     __syncthreads();
     // boxes in sorted order (separate pass: sbox currently holds candidate order, read via rec instead)
@@ -324,12 +422,17 @@ __global__ void __launch_bounds__(POST_NT) post_kernel(const PostArgs a) {
     }
     __syncthreads();
 
-    // ---- phase 3: per-class greedy NMS, one warp per class ---------------------------------------
+    // ---- phase 3: per-class greedy NMS (bitmask tiles): large classes by the whole CTA, the others one warp per class ------------
     {
         const int wid = tid >> 5;
         const float nthr_f = (float)a.nms_thres;
+        constexpr int BIG = 64;
+        for (int c = 0; c < a.nc; ++c)                                    // s_start is shared: every thread takes the same branches
+            if (s_start[c + 1] - s_start[c] > BIG)
+                block_nms_segment<MODE>(sbox, alive, s_start[c], s_start[c + 1], a.nms_thres, nthr_f, s_kbox, &s_nk);
         for (int c = wid; c < a.nc; c += POST_NW)
-            warp_nms_segment<MODE>(sbox, alive, s_start[c], s_start[c + 1], a.nms_thres, nthr_f);
+            if (s_start[c + 1] - s_start[c] <= BIG)
+                warp_nms_segment<MODE>(sbox, alive, s_start[c], s_start[c + 1], a.nms_thres, nthr_f);
     }
     __syncthreads();
 
