@@ -1,5 +1,6 @@
 #!/bin/bash
-# One GPU-box session: GPU test suite, smoke, bench (ours + reference arm), ncu launch list. Everything lands in gpurun_out/.
+# One GPU-box session (N = 1): GPU test suite, smoke, bench (reference arm + ours), the 320x256 configuration, and the ncu launch list of
+# a short bench run (shares per launch + DRAM bytes). Everything lands in gpurun_out/ (small files only).
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 nvidia-smi > gpurun_out/nvidia-smi.txt 2>&1
@@ -16,8 +17,9 @@ echo "bench 256 exit $?" >> gpurun_out/summary.txt
 timeout 600 python bench.py --batch 1 --steps 200 --warmup 20 --no-cpu-baseline > gpurun_out/bench_b1.log 2> gpurun_out/bench_b1.err
 echo "bench b1 exit $?" >> gpurun_out/summary.txt
 # every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
+K='regex:irb_kernel|irbtc_kernel|irbtc2_kernel|dwpw_tc_kernel|dense_tc_kernel|stem_kernel|wstem_kernel|wirb_kernel|upcat_kernel|upcat_tc_kernel|pw_kernel|post_kernel|compact_dets_kernel'
 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
-  timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"irb_kernel|irbtc_kernel|irbtc2_kernel|dwpw_tc_kernel|dense_kernel|dense_tc_kernel|stem_kernel|upcat_kernel|upcat_tc_kernel|pw_kernel|post_kernel" -c 400 --csv --log-file gpurun_out/launches.csv \
+  timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt

@@ -1,6 +1,6 @@
 """Turn the ncu launch list of one bench run (tools/gpu_round.sh: gpu__time_duration + dram bytes per launch) into the committed
-summaries: profiles/r01_launch_shares.txt (share of device time per fused group, to be compared with bench.py's CUDA-event shares)
-and profiles/r01_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic).
+summaries: profiles/r02_launch_shares.txt (share of device time per fused group, to be compared with bench.py's CUDA-event shares)
+and profiles/r02_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic).
 
     python tools/launch_report.py gpurun_out/launches.csv 640x512 256
 """
@@ -33,7 +33,7 @@ def main():
     n = len(GROUPS)
     last = max(i for i, l in enumerate(launches) if "post_kernel" in l["name"])
     step = launches[last - n + 1:last + 1]     # the last complete step: 30 forward groups + the head/NMS kernel
-    assert len(step) == n and "stem_kernel" in step[0]["name"], "no complete step in the launch list"
+    assert len(step) == n and "stem_kernel" in step[0]["name"], "no complete step in the launch list"      # wstem_kernel / stem_kernel
     tot = sum(l["gpu__time_duration.sum"] for l in step)
     out = ["share of device time among this library's kernels in the LAST step of the ncu launch list (%s, %s batch %d; cold-cache,"
            % (os.path.basename(path), workload, batch), "serialised launches: compare SHARES with bench.py's CUDA-event shares, not absolutes)",
@@ -45,9 +45,9 @@ def main():
         short = l["name"].split("(")[0].replace("void yf::", "").replace("yf::", "")[:44]
         out.append("%-10s %-44s %10.1f %6.1f%% %12.1f %12.1f" % (g, short, l["gpu__time_duration.sum"], 100 * l["gpu__time_duration.sum"] / tot, rd / 1e6, wr / 1e6))
     out.append("%-10s %-44s %10.1f" % ("total", "", tot))
-    open(os.path.join(ROOT, "profiles", "r01_launch_shares.txt"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(ROOT, "profiles", "r02_launch_shares.txt"), "w").write("\n".join(out) + "\n")
     json.dump({"workload": "%s b%d" % (workload, batch), "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none",
-               "bytes_per_launch": traffic}, open(os.path.join(ROOT, "profiles", "r01_traffic.json"), "w"), indent=1)
+               "bytes_per_launch": traffic}, open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w"), indent=1)
     print("\n".join(out))
 
 
