@@ -320,11 +320,12 @@ struct WstemCfg {
     static constexpr int RAWWU = 96;                           // uint8 box columns: image columns 2*x0 - 16 .. 2*x0 + 79
     static constexpr int RAWF = rup(RAWH * RAWW, 32);          // floats of one fp32 raw buffer (128-byte multiple)
     static constexpr int RAWU = rup(RAWH * RAWWU, 128);        // bytes of one uint8 box
-    static constexpr int C0W = 36, C0F = 8 * C0W;              // conv0 row buffer [8][36]: column 0 = output column x0 - 1
+    static constexpr int C0W = 40, C0F = 8 * C0W;              // conv0 row buffer [8][40] (two of them): column 0 = output column x0 - 1; 40:
+                                                               // the stage-0 stores of a 128-bit phase (4 strips x 2 channel pairs) hit 8 different bank groups
     static constexpr int DWS = OW + 4, DROW = CMID * DWS;
     static constexpr int OFF_W0 = 0, OFF_B0 = 72, OFF_W1 = 80, OFF_B1 = 144, OFF_WD = 152, OFF_BD = 224, OFF_W2 = 232, OFF_B2 = 264;
     static constexpr int WFLOATS = 268;
-    template <bool U8> __host__ __device__ static constexpr int warp_bytes() { return (U8 ? 2 * RAWU + RAWF * 4 : 2 * RAWF * 4) + C0F * 4 + 2 * DROW * 4; }
+    template <bool U8> __host__ __device__ static constexpr int warp_bytes() { return (U8 ? 2 * RAWU + RAWF * 4 : 2 * RAWF * 4) + 2 * C0F * 4 + 2 * DROW * 4; }
     template <bool U8> __host__ __device__ static constexpr int smem_bytes() { return NW * warp_bytes<U8>() + (U8 ? 1024 : 0) + 128; }
     static_assert(smem_bytes<false>() <= 227 * 1024 && smem_bytes<true>() <= 227 * 1024, "does not fit shared memory");
 };
@@ -341,8 +342,8 @@ wstem_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y, co
     unsigned char* wb = base + (size_t)warp * C::template warp_bytes<U8>();
     unsigned char* Ub = wb;                                                     // U8: two uint8 boxes
     float* Rf = reinterpret_cast<float*>(wb + (U8 ? 2 * C::RAWU : 0));          // fp32 raw rows: U8 one normalised copy, else two boxes
-    float* C0 = Rf + (U8 ? 1 : 2) * C::RAWF;
-    float* Db = C0 + C::C0F;
+    float* C0b = Rf + (U8 ? 1 : 2) * C::RAWF;                                   // two conv0 row buffers
+    float* Db = C0b + 2 * C::C0F;
     float* Lut = reinterpret_cast<float*>(base + (size_t)C::NW * C::template warp_bytes<U8>());
     if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); }
     if (threadIdx.x == 0) tma_prefetch_desc(&xmap);
@@ -351,16 +352,19 @@ wstem_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y, co
     mbar_fence_init();
     __syncthreads();
 
-    const int pl = lane >> 3, sl = lane & 7;                    // stage 0 / expand / depthwise: channel pair, column strip
+    const int pl = lane >> 3, sl = lane & 7;                    // expand / depthwise: channel pair, column strip
     const int pn = lane >> 3, pq = lane & 7;                    // projection: output channel, pixel group
+    // stage 0 (conv0) uses its own partition: the 8 lanes of a 128-bit shared-memory phase are 4 strips x 2 channel pairs, so their
+    // raw-row loads (32 bytes apart per strip) span 128 bytes — with 8 strips per phase they were 2-way bank conflicted
+    const int s0 = ((lane >> 3) & 1) * 4 + (lane & 3), c0p = ((lane >> 4) << 1) | ((lane >> 2) & 1);
     float2 w0[9], w1[8], wd[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) w0[t] = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_W0 + t * 8) + pl);
+    for (int t = 0; t < 9; ++t) w0[t] = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_W0 + t * 8) + c0p);
 #pragma unroll
     for (int k = 0; k < 8; ++k) w1[k] = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_W1 + k * 8) + pl);
 #pragma unroll
     for (int t = 0; t < 9; ++t) wd[t] = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_WD + t * 8) + pl);
-    const float2 b0 = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_B0) + pl);
+    const float2 b0 = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_B0) + c0p);
     const float2 b1 = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_B1) + pl);
     const float2 bd = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_BD) + pl);
     const float b2 = __ldg(wts + C::OFF_B2 + pn);
@@ -456,48 +460,55 @@ wstem_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y, co
             } else {
                 Rs = Rf + (g & 1) * C::RAWF;
             }
+            // stage 0: conv0 row of box row `row` (columns x0 - 1 + [0, 34)) from raw rows 2*row .. 2*row + 2 -> C0 buffer `row & 1`.
+            // It runs ONE ROW AHEAD of the pipeline below (row 0 of a box before the loop, row rr + 1 inside iteration rr), so its
+            // loads and FMAs interleave with the expand / depthwise of the current row and one __syncwarp per row covers both D and C0.
+            auto stage0 = [&](int row) {
+                const int iy0 = y0 - 1 + c * RC + row;
+                const float mrow = (unsigned)iy0 < (unsigned)Hout ? 1.f : 0.f;     // rows outside the map are zero (the depthwise pads E = f(conv0))
+                float* C0 = C0b + (row & 1) * C::C0F;
+                float2 a0[4];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    // conv0 column c reads buffer columns 1 + 2c .. 3 + 2c; c = 4*s0 + i
+                    const float* rp = Rs + (2 * row + dy) * C::RAWW + 8 * s0;
+                    const float4 va = ld4(rp), vb = ld4(rp + 4);
+                    const float2 vc = *reinterpret_cast<const float2*>(rp + 8);
+                    const float v[10] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) a0[i] = fma2s(w0[dy * 3 + dx], v[1 + 2 * i + dx], (dy == 0 && dx == 0) ? b0 : a0[i]);
+                }
+                float2 q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = mul2s(relu2(a0[i]), mrow);
+                st4(C0 + (2 * c0p) * C::C0W + 4 * s0, make_float4(q[0].x, q[1].x, q[2].x, q[3].x));
+                st4(C0 + (2 * c0p + 1) * C::C0W + 4 * s0, make_float4(q[0].y, q[1].y, q[2].y, q[3].y));
+                if (lane < 8) {
+                    float2 ax = b0x;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const float* rp = Rs + (2 * row + dy) * C::RAWW + 1 + 2 * xc;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) ax = fma2s(w0x[dy * 3 + dx], rp[dx], ax);
+                    }
+                    ax = mul2s(relu2(ax), mrow);
+                    C0[(2 * xp) * C::C0W + xc] = ax.x;
+                    C0[(2 * xp + 1) * C::C0W + xc] = ax.y;
+                }
+            };
+            stage0(0);
+            __syncwarp();
 #pragma unroll
             for (int rr = 0; rr < RC; ++rr) {
                 const int r = c * RC + rr;
                 const int iy = y0 - 1 + r;                      // expanded row (H/2 map)
                 const int par = rr & 1;
                 project(Db + (par ^ 1) * C::DROW);
+                if (rr + 1 < RC) stage0(rr + 1);
                 const bool row_in = (unsigned)iy < (unsigned)Hout;
-                const float mrow = row_in ? 1.f : 0.f;
-                // ---- stage 0: conv0 row iy, columns x0 - 1 + [0, 34), from raw rows 2*rr .. 2*rr + 2 of the box ----------------
-                {
-                    float2 a0[4];
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        // conv0 column c reads buffer columns 1 + 2c .. 3 + 2c; c = 4*sl + i
-                        const float* rp = Rs + (2 * rr + dy) * C::RAWW + 8 * sl;
-                        const float4 va = ld4(rp), vb = ld4(rp + 4);
-                        const float2 vc = *reinterpret_cast<const float2*>(rp + 8);
-                        const float v[10] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) a0[i] = fma2s(w0[dy * 3 + dx], v[1 + 2 * i + dx], (dy == 0 && dx == 0) ? b0 : a0[i]);
-                    }
-                    float2 q[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) q[i] = mul2s(relu2(a0[i]), mrow);      // rows outside the map are zero (the depthwise pads E, and E = f(conv0))
-                    st4(C0 + (2 * pl) * C::C0W + 4 * sl, make_float4(q[0].x, q[1].x, q[2].x, q[3].x));
-                    st4(C0 + (2 * pl + 1) * C::C0W + 4 * sl, make_float4(q[0].y, q[1].y, q[2].y, q[3].y));
-                    if (lane < 8) {
-                        float2 ax = b0x;
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            const float* rp = Rs + (2 * rr + dy) * C::RAWW + 1 + 2 * xc;
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) ax = fma2s(w0x[dy * 3 + dx], rp[dx], ax);
-                        }
-                        ax = mul2s(relu2(ax), mrow);
-                        C0[(2 * xp) * C::C0W + xc] = ax.x;
-                        C0[(2 * xp + 1) * C::C0W + xc] = ax.y;
-                    }
-                }
-                __syncwarp();
+                const float* C0 = C0b + (rr & 1) * C::C0F;
                 // ---- expand (conv1_2) over this lane's window of the conv0 row ------------------------------------------------
                 const float2 b1r = row_in ? b1 : make_float2(0.f, 0.f);
                 float2 e[NC];
