@@ -116,3 +116,23 @@ def test_config_variants():
     assert len(yf.config_params["io_params"]["anchors"]) == 3           # untouched module-level dict
     with pytest.raises(ValueError):
         yf.config_for("1x1")
+
+
+def test_bench_work_model_matches_the_survey():
+    """bench.py's per-group algorithmic work (the numerators of every roofline figure) against SURVEY.md §8d: 945.8 MFLOP and
+    19 763 200 B of unique fp32 activations per 640x512 image for the reference's layers (the bench counts the executed work of the
+    composed heads — one 1x1 instead of two — and adds the folded weights once per launch)."""
+    import bench
+    for (H, W), macs_ref, act_bytes in (((512, 640), 472.9e6, 19763200), ((256, 320), 118.22e6, 4940800)):
+        G = bench.group_work(H, W, 24)
+        assert len(G) == 30 and [g["name"] for g in G][:3] == ["conv1_4", "res1_1", "conv2_1"]
+        px = lambda d: (H // d) * (W // d)
+        # the two 1x1 convs folded into the heads on the host (conv5_6: 128x128 at /32, conv4_1_5: 96x96 at /16)
+        composed = px(32) * 128 * 128 + px(16) * 96 * 96
+        macs = sum(g["macs"] for g in G)
+        assert abs(macs + composed - macs_ref) / macs_ref < 2e-3
+        # bytes: the survey's plan fuses each neck branch into one kernel; here conv5_2 / conv5_4 / conv4_1_3 are launches of their own,
+        # so their outputs are written and read once more (96 + 128 channels at /32, 96 at /16), plus every folded weight once
+        extra = 4 * 2 * ((96 + 128) * px(32) + 96 * px(16))
+        total = sum(g["bytes"] for g in G)
+        assert act_bytes <= total <= act_bytes + extra + 4 * 346356
