@@ -16,6 +16,7 @@
 #include "yf_kernels.cuh"
 #include "yf_post.cuh"
 #include "yf_tc.cuh"
+#include "yf_tct.cuh"
 #include "yf_wirb.cuh"
 #include "yf_tcpw.cuh"
 #include "yf_tcup.cuh"
@@ -283,6 +284,10 @@ using CfgRes3b = YF_CFGRES3B;
 #define YF_CFGRES3B_TC IrbTcCfg<16, 96, 16, YF_TC3_TH, YF_TC3_TW, YF_TC3_MC, YF_TC3_RH, YF_TC3_NWW, true, YF_TC3_E1ALL, YF_TC3_OCC>
 #endif
 using CfgRes3bTc = YF_CFGRES3B_TC;
+#ifndef YF_USE_TCT
+#define YF_USE_TCT 1    // 1: res3_3..6 run on the channel-lane kernel (yf_tct.cuh) at every batch size (one kernel: results do not depend on the batch)
+#endif
+using CfgRes3bTt = IrbTtCfg<16, 96, 16, true>;
 #ifndef YF_CFGRES4_TC
 #define YF_CFGRES4_TC IrbTcCfg<24, 136, 24, 8, 20, 32, 4, 10, true, true>
 #endif
@@ -544,6 +549,22 @@ void launch_irbtc_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaSt
     else if (2 * big <= g.nsm) launch_irbtc<CS>(g, x, u8, B, st);
     else launch_irbtc<CB>(g, x, u8, B, st);
 }
+template <class C>
+void launch_irbt(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    TmaCache* tc = g.tc;
+    if (tc->ptr != g.x || tc->B != B) {
+        tc->failed = tma_make_map4(&tc->map, g.x, 4, B, C::CIN, g.Hin, g.Win, C::RW, C::HR, C::CIN) != 0;
+        tc->ptr = g.x; tc->B = B;
+    }
+    if (tc->failed) return;
+    const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
+    const int total = B * tx * ty;
+    const int grid = total < g.nsm ? total : g.nsm;
+    irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+}
+template <class C>
+cudaError_t init_irbt() { return cudaFuncSetAttribute(irbt_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
+template <class C> int occ_irbt() { return occ_of(irbt_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C> int occ_irbtc() { return occ_of(irbtc_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
 cudaError_t init_irbtc() { return cudaFuncSetAttribute(irbtc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
@@ -830,6 +851,27 @@ int64_t pack_irbtc(std::vector<float>& out, const Folded& f, const std::string& 
             for (int n = 0; n < C::COUT; ++n)
                 put_kmajor_split(cb + C::OFF_W2, cb + C::OFF_W2 + C::COUTP * C::MC, n, ml, C::MC, f.w(n2)[n * C::CMID + m]);
         }
+    }
+    for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
+    return off;
+}
+
+// channel-lane tensor-core block (yf_tct.cuh):
+// [W1hi: 128 x KX][W1lo][W2: (hi | lo) x CMID][wd: CMID x 9][bd][b2]; column CIN of W1 is the expand bias (the ones channel)
+template <class C>
+int64_t pack_irbt(std::vector<float>& out, const Folded& f, const std::string& n1, const std::string& nd, const std::string& n2) {
+    pad4(out);
+    while (out.size() % 32) out.push_back(0.f);
+    const int64_t off = (int64_t)out.size();
+    out.resize(off + C::WFLOATS, 0.f);
+    float* o = out.data() + off;
+    for (int m = 0; m < C::CMID; ++m) {
+        for (int k = 0; k < C::CIN; ++k) put_kmajor_split(o + C::OFF_W1H, o + C::OFF_W1L, m, k, C::KX, f.w(n1)[m * C::CIN + k]);
+        put_kmajor_split(o + C::OFF_W1H, o + C::OFF_W1L, m, C::CIN, C::KX, f.b(n1)[m]);
+        for (int t = 0; t < 9; ++t) o[C::OFF_WD + m * 9 + t] = f.w(nd)[m * 9 + t];
+        o[C::OFF_BD + m] = f.b(nd)[m];
+        for (int n = 0; n < C::COUT; ++n)
+            put_kmajor_split(o + C::OFF_W2, o + C::OFF_W2 + C::COUTP * C::CMID, n, m, C::CMID, f.w(n2)[n * C::CMID + m]);
     }
     for (int n = 0; n < C::COUT; ++n) o[C::OFF_B2 + n] = f.b(n2)[n];
     return off;
@@ -1152,10 +1194,15 @@ static void build_plan(yf_ctx* ctx) {
     if (ctx->variant == YF_VARIANT_LITE) { Group g{}; g.name = "conv3_4"; g.launch = &launch_lite34; g.out_ch = 16; chain(g, 8, 8); }
     else chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
 #if YF_USE_TC
-    { Group g = make_irbtc<CfgRes3bTc>("res3_3", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
-    { Group g = make_irbtc<CfgRes3bTc>("res3_4", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
-    { Group g = make_irbtc<CfgRes3bTc>("res3_5", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
-    { Group g = make_irbtc<CfgRes3bTc>("res3_6", 16); g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>; chain(g, 8, 8); }
+    for (const char* n : {"res3_3", "res3_4", "res3_5", "res3_6"}) {
+        Group g = make_irbtc<CfgRes3bTc>(n, 16);
+#if YF_USE_TCT
+        g.launch = &launch_irbt<CfgRes3bTt>; g.occupancy = &occ_irbt<CfgRes3bTt>;
+#else
+        g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>;
+#endif
+        chain(g, 8, 8);
+    }
 #else
     chain(make_irb<CfgRes3b>("res3_3", 16), 8, 8);
     chain(make_irb<CfgRes3b>("res3_4", 16), 8, 8);
@@ -1275,7 +1322,7 @@ extern "C" int yf_create_variant(yf_ctx** out, int device, int in_ch, int num_cl
         cudaFuncSetAttribute(post_kernel<YF_MODE_VALIDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         cudaFuncSetAttribute(post_kernel<POST_SRC_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbt<CfgRes3bTt>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -1351,7 +1398,8 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     offs.push_back(ctx->variant == YF_VARIANT_LITE ? pack_lite34(P, f) : pack_irb<CfgWide3>(P, f, "conv3_2", "conv3_3", "conv3_4", "", 0));
 #if YF_USE_TC
     for (const char* n : {"res3_3", "res3_4", "res3_5", "res3_6"})
-        offs.push_back(pack_irbtc<CfgRes3bTc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
+        offs.push_back(YF_USE_TCT ? pack_irbt<CfgRes3bTt>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3")
+                                  : pack_irbtc<CfgRes3bTc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
 #else
     res(CfgRes3b{}, "res3_3"); res(CfgRes3b{}, "res3_4"); res(CfgRes3b{}, "res3_5"); res(CfgRes3b{}, "res3_6");
 #endif
