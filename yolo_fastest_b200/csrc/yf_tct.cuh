@@ -16,9 +16,9 @@
 //
 // Tile = 8 x 16 output pixels (128 = one MMA tile of the project GEMM), halo 10 x 18 = 180 -> N = 192. TMEM: two E^T buffers
 // (2 x 192 columns) + two O buffers (2 x 32): the expand GEMM of tile t + 1 runs while the workers are on tile t, the output
-// epilogue of tile t - 1 runs behind the depthwise of tile t. 16 warps: warp % 4 = TMEM lane quarter; quarters 0..2 (12 warps) are
-// workers — channel = 32 * quarter + lane, warp / 4 = which pair of output rows — quarter 3 holds two input-staging warps, the warp
-// that runs the output epilogue of TMEM lane quarter 3, and the tensor-core warp. fp32 parity through 3xTF32 exactly as in yf_tc.cuh.
+// epilogue of tile t - 1 runs behind the depthwise of tile t. 19 warps, warp % 4 = TMEM lane quarter: of the first 16, quarters 0..2
+// (12 warps) are workers — channel = 32 * quarter + lane, warp / 4 = which pair of output rows — and quarter 3 holds two
+// input-staging warps, one output-epilogue warp and the tensor-core warp; warps 16..18 are the output-epilogue warps of quarters 0..2. fp32 parity through 3xTF32 exactly as in yf_tc.cuh.
 //
 // Operand layouts: W1^T (A) and X^T (B) are both K-major, un-swizzled core matrices [row / 8][k / 4][row % 8][k % 4] — the layout the
 // weight operands of every other kernel use (validated there); the input staging writes one 16-byte core-matrix row per
@@ -44,6 +44,13 @@ __device__ __forceinline__ void tmem_ld_row18(uint32_t taddr, float (&v)[18]) {
     for (int i = 0; i < 18; ++i) v[i] = fmaxf(__uint_as_float(r[i]), 0.f);       // ReLU; the bias came through the GEMM
 }
 
+// -DYF_TC_TRACE -DYF_TCT_TRACE: CTA 0 records clock64() per tile: slots 0..5 worker warp 0, 6..9 tensor-core thread, 10..13 staging warp 0
+#if defined(YF_TC_TRACE) && defined(YF_TCT_TRACE)
+#define TT_TRACE(tile, ev) do { if (blockIdx.x == 0 && (tile) < 64) g_tc_trace[(tile) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TT_TRACE(tile, ev) do { } while (0)
+#endif
+
 template <int CIN_, int CMID_, int COUT_, bool RES_>
 struct IrbTtCfg {
     static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_;
@@ -52,7 +59,7 @@ struct IrbTtCfg {
     static constexpr int HR = TH + 2, HW = TW + 2, HPIX = HR * HW;        // halo tile, pixel n = r * HW + j
     static constexpr int NPX = rup(HPIX, 16);                             // N of the expand MMA
     static constexpr int KX = CIN + 8;                                    // + the ones channel (and 7 zero channels: K advances by 8)
-    static constexpr int NWARP = 16, NT = NWARP * 32;
+    static constexpr int NWARP = 19, NT = NWARP * 32;                     // 12 workers, 2 staging, tensor-core warp, 4 epilogue warps (one per TMEM lane quarter)
     static constexpr int NWORK = 12, NAUX = 2, NTA = NAUX * 32;         // worker warps; input-staging warps (a third quarter-3 warp runs that quarter's output epilogue)
     static constexpr int COUTP = rup(COUT, 16);
     static constexpr int KB3 = (OPIX / 32) * 256;                         // floats per 8-channel block of the operand D
@@ -122,17 +129,26 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
     };
     const size_t plane = (size_t)H * W;
 
-    // output epilogue of tile ti for the 32 pixels of TMEM lane quarter q (thread = pixel): O hi + correction columns + b2 (+ residual) -> HBM
-    auto epilogue = [&](int ti) {
+    // Output epilogue of tile ti for the 32 pixels of TMEM lane quarter q (thread = pixel), in two halves so that the HBM latency of the
+    // residual is not on the caller's path: epi_fetch (address + residual loads) is issued a phase early, epi_store reads O (hi +
+    // correction columns), adds b2 and the residual and writes the tile.
+    float er[C::RES ? C::COUT : 1];
+    size_t eoff = 0;
+    bool eok = false;
+    auto epi_fetch = [&](int ti) {
         int b, oy0, ox0;
         origin(ti, b, oy0, ox0);
         const int p = q * 32 + lane, gy = oy0 + (p >> 4), gx = ox0 + (p & 15);
-        const bool ok = gy < H && gx < W;
-        const size_t off = ((size_t)b * C::COUT * H + min(gy, H - 1)) * W + min(gx, W - 1);
-        float r[C::COUT];
+        eok = gy < H && gx < W;
+        eoff = ((size_t)b * C::COUT * H + min(gy, H - 1)) * W + min(gx, W - 1);
+        if (C::RES) {
 #pragma unroll
-        for (int i = 0; i < C::COUT; ++i) r[i] = C::RES ? __ldg(x + off + i * plane) : 0.f;
+            for (int i = 0; i < C::COUT; ++i) er[i] = __ldg(x + eoff + i * plane);
+        }
+    };
+    auto epi_store = [&](int ti) {
         const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + C::TM_O + (ti & 1) * 2 * C::COUTP;
+        float r[C::COUT];
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < C::COUT; c0 += 8) {
@@ -140,14 +156,14 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
             tmem_ld8(ta + c0, vh);
             tmem_ld8(ta + C::COUTP + c0, vl);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r[c0 + i] += (vh[i] + vl[i]) + __ldg(wts + C::OFF_B2 + c0 + i);
+            for (int i = 0; i < 8; ++i) r[c0 + i] = (vh[i] + vl[i]) + __ldg(wts + C::OFF_B2 + c0 + i) + (C::RES ? er[c0 + i] : 0.f);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ofree[ti & 1]);
-        if (ok) {
+        if (eok) {
 #pragma unroll
-            for (int i = 0; i < C::COUT; ++i) y[off + i * plane] = r[i];
+            for (int i = 0; i < C::COUT; ++i) y[eoff + i * plane] = r[i];
         }
     };
 
@@ -195,16 +211,29 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
                     mbar_wait(&xfull, (t + 1) & 1);
                     if (t + 1 >= 2) mbar_wait(&efree[(t + 1) & 1], (((t + 1) >> 1) - 1) & 1);
                     tc_fence_after();
+                    TT_TRACE(t, 6);
                     expand(t + 1);
+                    TT_TRACE(t, 7);
                 }
                 mbar_wait(&dfull, t & 1);
                 if (t >= 2) mbar_wait(&ofree[t & 1], ((t >> 1) - 1) & 1);
                 tc_fence_after();
+                TT_TRACE(t, 8);
                 project(t);
+                TT_TRACE(t, 9);
             }
         }
+    } else if (warp >= 16 || (q == 3 && g == C::NAUX)) {
+        // ================= output epilogue warps, one per TMEM lane quarter (warps 16, 17, 18 and 11): each waits for EVERY phase of
+        // ofull in order (a parity wait that skipped a phase could pass on the phase before), and the next completion of the same
+        // barrier needs the warp's own ofree arrival =================
+        for (int t = 0; t < ntile; ++t) {
+            epi_fetch(t);
+            mbar_wait(&ofull[t & 1], (t >> 1) & 1);            // project MMA of tile t complete
+            epi_store(t);
+        }
     } else if (q == 3) {
-        // ================= input staging warps (and the output epilogue of TMEM lane quarter 3) =================
+        // ================= input staging warps =================
         // Staging: the raw halo box of tile t (16 channels x 10 rows x 24 columns, zero outside the image) arrives by TMA two tiles ahead;
         // these warps split it into the expand operand X^T (hi | lo, one 16-byte core-matrix row per pixel and 4 channels) and set the
         // ones channel. A thread's items (halo pixel n, channel group kg) are the same every tile: offsets precomputed.
@@ -253,23 +282,20 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
             __syncwarp();
             if (lane == 0) { mbar_arrive(&xfull); mbar_arrive(&rawfree[ti & 1]); }
         };
-        if (g == C::NAUX) {
-            // quarter 3's output epilogue, ONE warp for every tile: it waits for each phase of ofull in order (a parity wait that skipped a
-            // phase could pass on the phase before), and the next completion of the same barrier needs this warp's own ofree arrival
-            for (int t = 0; t < ntile; ++t) {
-                mbar_wait(&ofull[t & 1], (t >> 1) & 1);        // project MMA of tile t complete
-                epilogue(t);
-            }
-        } else {
+        {
             if (ta == 0) {
                 tma_prefetch_desc(&xmap);
                 if (ntile > 0) issue(0);
                 if (ntile > 1) issue(1);
             }
             for (int t = 0; t < ntile; ++t) {
+                if (ta == 0) TT_TRACE(t, 10);
                 mbar_wait(&rawfull[t & 1], (t >> 1) & 1);      // the box of tile t has landed
+                if (ta == 0) TT_TRACE(t, 11);
                 if (t >= 1) mbar_wait(&xfree, (t - 1) & 1);    // the expand MMA of tile t - 1 has read X
+                if (ta == 0) TT_TRACE(t, 12);
                 put(t);
+                if (ta == 0) TT_TRACE(t, 13);
                 if (ta == 0 && t + 2 < ntile) {
                     mbar_wait(&rawfree[t & 1], (t >> 1) & 1);  // both staging warps are done with this buffer
                     issue(t + 2);
@@ -290,8 +316,10 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         for (int t = 0; t < ntile; ++t) {
             const uint32_t te = tmem + lane_base + C::TM_E + (t & 1) * C::NPX + (2 * g) * C::HW;
+            if (tid == 0) TT_TRACE(t, 0);
             mbar_wait(&efull[t & 1], (t >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) TT_TRACE(t, 1);
             float e[3][18], a[2][16];
             tmem_ld_row18(te, e[0]);
             tmem_ld_row18(te + C::HW, e[1]);
@@ -316,7 +344,9 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
                 }
             }
             // everything above overlapped the project MMA of tile t - 1; only the operand stores have to wait for it
+            if (tid == 0) TT_TRACE(t, 2);
             if (t >= 1) mbar_wait(&dfree, (t - 1) & 1);
+            if (tid == 0) TT_TRACE(t, 3);
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll
@@ -345,11 +375,8 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&dfull);
-            if (t >= 1 && g == ((t - 1) & 3)) epilogue(t - 1);          // its project MMA completed before this tile's first D store
-        }
-        if (ntile > 0 && g == ((ntile - 1) & 3)) {
-            mbar_wait(&dfree, (ntile - 1) & 1);
-            epilogue(ntile - 1);
+            if (tid == 0) TT_TRACE(t, 4);
+            if (tid == 0) TT_TRACE(t, 5);
         }
     }
     tc_fence_before();
