@@ -285,13 +285,23 @@ using CfgRes3b = YF_CFGRES3B;
 #endif
 using CfgRes3bTc = YF_CFGRES3B_TC;
 #ifndef YF_USE_TCT
-#define YF_USE_TCT 1    // 1: res3_3..6 run on the channel-lane kernel (yf_tct.cuh) at every batch size (one kernel: results do not depend on the batch)
+#define YF_USE_TCT 1    // 1: res3_3..6 and res4_1..4 run on the channel-lane kernel (yf_tct.cuh) at every batch size (one kernel: results do not depend on the batch)
 #endif
-using CfgRes3bTt = IrbTtCfg<16, 96, 16, true>;
+#ifndef YF_USE_TCT_A
+#define YF_USE_TCT_A 1  // 1: so do the 48-mid-channel groups res3_1, res3_2 and conv3_2 -> conv3_4
+#endif
+// IrbTtCfg<CIN, CMID, COUT, tile height (x 8 columns), RES, TMEM lane quarter of channel 128>
+using CfgRes3bTt = IrbTtCfg<16, 96, 16, 16, true>;
+using CfgRes4Tt = IrbTtCfg<24, 136, 24, 8, true, 2>;
+using CfgRes3aTt = IrbTtCfg<8, 48, 8, 16, true>;
+using CfgWide3Tt = IrbTtCfg<8, 48, 16, 16, false>;
 #ifndef YF_CFGRES4_TC
 #define YF_CFGRES4_TC IrbTcCfg<24, 136, 24, 8, 20, 32, 4, 10, true, true>
 #endif
 using CfgRes4Tc = YF_CFGRES4_TC;
+// res4 maps are 1/16 of the input: their rows are a multiple of 16 bytes (what a TMA tensor map needs) only when the input width is a
+// multiple of 64. Other widths (416 -> 26 columns) keep the pixel-lane kernel; both weight blocks sit in the group's blob.
+constexpr int64_t RES4_TT_OFF = (CfgRes4Tc::WFLOATS + 31) / 32 * 32;
 #ifndef YF_USE_TC
 #define YF_USE_TC 1     // 1: res3_3..6 and res4_1..4 run on the tcgen05 kernel (yf_tc.cuh); 0: everything on the FFMA engine (libyf_b200_ffma.so)
 #endif
@@ -550,7 +560,7 @@ void launch_irbtc_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaSt
     else launch_irbtc<CB>(g, x, u8, B, st);
 }
 template <class C>
-void launch_irbt(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+void launch_irbt(const GroupArgs& g, const void*, bool, int B, cudaStream_t st, int64_t w_off = 0) {
     TmaCache* tc = g.tc;
     if (tc->ptr != g.x || tc->B != B) {
         tc->failed = tma_make_map4(&tc->map, g.x, 4, B, C::CIN, g.Hin, g.Win, C::RW, C::HR, C::CIN) != 0;
@@ -560,10 +570,17 @@ void launch_irbt(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) 
     const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
     const int total = B * tx * ty;
     const int grid = total < g.nsm ? total : g.nsm;
-    irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+    irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.w + w_off, g.Hout, g.Wout, tx, ty, total);
 }
 template <class C>
 cudaError_t init_irbt() { return cudaFuncSetAttribute(irbt_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
+template <class C> void launch_irbt0(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) { launch_irbt<C>(g, x, u8, B, st, 0); }
+// res4: the channel-lane kernel where the map's rows can be a TMA tensor (shape only: the choice never depends on the batch)
+template <class CT, class CB, class CS, class CXS>
+void launch_res4_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
+    if (g.Wout % 4 == 0) launch_irbt<CT>(g, x, u8, B, st, RES4_TT_OFF);
+    else launch_irbtc_auto<CB, CS, CXS>(g, x, u8, B, st);
+}
 template <class C> int occ_irbt() { return occ_of(irbt_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C> int occ_irbtc() { return occ_of(irbtc_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C>
@@ -1189,15 +1206,22 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes2>("res2_2", 8), 4, 4);
     chain(make_irb<CfgDown2>("conv3_1", 8), 4, 8);
 #endif
-    chain(make_irb<CfgRes3a>("res3_1", 8), 8, 8);
-    chain(make_irb<CfgRes3a>("res3_2", 8), 8, 8);
+    for (const char* n : {"res3_1", "res3_2"}) {
+        Group g = make_irb<CfgRes3a>(n, 8);
+        if (YF_USE_TC && YF_USE_TCT_A) { g.launch = &launch_irbt0<CfgRes3aTt>; g.occupancy = &occ_irbt<CfgRes3aTt>; }
+        chain(g, 8, 8);
+    }
     if (ctx->variant == YF_VARIANT_LITE) { Group g{}; g.name = "conv3_4"; g.launch = &launch_lite34; g.out_ch = 16; chain(g, 8, 8); }
-    else chain(make_irb<CfgWide3>("conv3_4", 16), 8, 8);
+    else {
+        Group g = make_irb<CfgWide3>("conv3_4", 16);
+        if (YF_USE_TC && YF_USE_TCT_A) { g.launch = &launch_irbt0<CfgWide3Tt>; g.occupancy = &occ_irbt<CfgWide3Tt>; }
+        chain(g, 8, 8);
+    }
 #if YF_USE_TC
     for (const char* n : {"res3_3", "res3_4", "res3_5", "res3_6"}) {
         Group g = make_irbtc<CfgRes3bTc>(n, 16);
 #if YF_USE_TCT
-        g.launch = &launch_irbt<CfgRes3bTt>; g.occupancy = &occ_irbt<CfgRes3bTt>;
+        g.launch = &launch_irbt0<CfgRes3bTt>; g.occupancy = &occ_irbt<CfgRes3bTt>;
 #else
         g.launch = &launch_irbtc_auto<CfgRes3bTc, CfgRes3bTcS, CfgRes3bTcXS>;
 #endif
@@ -1211,10 +1235,15 @@ static void build_plan(yf_ctx* ctx) {
 #endif
     { Group g = make_irb<CfgDown3>("conv4_1", 24); g.launch = &launch_irb_auto<CfgDown3, CfgDown3N>; chain(g, 8, 16); }
 #if YF_USE_TC
-    { Group g = make_irbtc<CfgRes4Tc>("res4_1", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>; chain(g, 16, 16); }
-    { Group g = make_irbtc<CfgRes4Tc>("res4_2", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>; chain(g, 16, 16); }
-    { Group g = make_irbtc<CfgRes4Tc>("res4_3", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>; chain(g, 16, 16); }
-    { Group g = make_irbtc<CfgRes4Tc>("res4_4", 24); g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>; chain(g, 16, 16); }
+    for (const char* n : {"res4_1", "res4_2", "res4_3", "res4_4"}) {
+        Group g = make_irbtc<CfgRes4Tc>(n, 24);
+#if YF_USE_TCT
+        g.launch = &launch_res4_auto<CfgRes4Tt, CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>;
+#else
+        g.launch = &launch_irbtc_auto<CfgRes4Tc, CfgRes4TcS, CfgRes4TcXS>;
+#endif
+        chain(g, 16, 16);
+    }
 #else
     chain(make_irb<CfgRes4>("res4_1", 24), 16, 16);
     chain(make_irb<CfgRes4>("res4_2", 24), 16, 16);
@@ -1322,7 +1351,7 @@ extern "C" int yf_create_variant(yf_ctx** out, int device, int in_ch, int num_cl
         cudaFuncSetAttribute(post_kernel<YF_MODE_VALIDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         cudaFuncSetAttribute(post_kernel<POST_SRC_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbt<CfgRes3bTt>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbt<CfgRes3bTt>(), init_irbt<CfgRes4Tt>(), init_irbt<CfgRes3aTt>(), init_irbt<CfgWide3Tt>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -1394,8 +1423,13 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     res(CfgRes2{}, "res2_1"); res(CfgRes2{}, "res2_2");
     offs.push_back(pack_irb<CfgDown2>(P, f, "conv2_2", "conv2_3", "conv3_1", "", 0));
 #endif
-    res(CfgRes3a{}, "res3_1"); res(CfgRes3a{}, "res3_2");
-    offs.push_back(ctx->variant == YF_VARIANT_LITE ? pack_lite34(P, f) : pack_irb<CfgWide3>(P, f, "conv3_2", "conv3_3", "conv3_4", "", 0));
+    if (YF_USE_TC && YF_USE_TCT_A) {
+        offs.push_back(pack_irbt<CfgRes3aTt>(P, f, "res3_1.conv1", "res3_1.conv2", "res3_1.conv3"));
+        offs.push_back(pack_irbt<CfgRes3aTt>(P, f, "res3_2.conv1", "res3_2.conv2", "res3_2.conv3"));
+    } else { res(CfgRes3a{}, "res3_1"); res(CfgRes3a{}, "res3_2"); }
+    offs.push_back(ctx->variant == YF_VARIANT_LITE ? pack_lite34(P, f)
+                   : (YF_USE_TC && YF_USE_TCT_A) ? pack_irbt<CfgWide3Tt>(P, f, "conv3_2", "conv3_3", "conv3_4")
+                                                 : pack_irb<CfgWide3>(P, f, "conv3_2", "conv3_3", "conv3_4", "", 0));
 #if YF_USE_TC
     for (const char* n : {"res3_3", "res3_4", "res3_5", "res3_6"})
         offs.push_back(YF_USE_TCT ? pack_irbt<CfgRes3bTt>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3")
@@ -1406,7 +1440,11 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     offs.push_back(pack_irb<CfgDown3>(P, f, "conv3_5", "conv3_6", "conv4_1", "", 0));
 #if YF_USE_TC
     for (const char* n : {"res4_1", "res4_2", "res4_3", "res4_4"})
+    {
         offs.push_back(pack_irbtc<CfgRes4Tc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
+        if (YF_USE_TCT && pack_irbt<CfgRes4Tt>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3") != offs.back() + RES4_TT_OFF)
+            { set_err(&ctx->err, "internal: res4 weight blocks at an unexpected offset"); return YF_ERR_STATE; }
+    }
 #else
     res(CfgRes4{}, "res4_1"); res(CfgRes4{}, "res4_2"); res(CfgRes4{}, "res4_3"); res(CfgRes4{}, "res4_4");
 #endif
