@@ -293,8 +293,12 @@ using CfgRes3bTc = YF_CFGRES3B_TC;
 // IrbTtCfg<CIN, CMID, COUT, tile height (x 8 columns), RES, TMEM lane quarter of channel 128>
 using CfgRes3bTt = IrbTtCfg<16, 96, 16, 16, true>;
 using CfgRes4Tt = IrbTtCfg<24, 136, 24, 8, true, 2>;
-using CfgRes3aTt = IrbTtCfg<8, 48, 8, 16, true>;
-using CfgWide3Tt = IrbTtCfg<8, 48, 16, 16, false>;
+#ifndef YF_TCT_A_TH
+#define YF_TCT_A_TH 16      // measured: 8-row tiles at two CTAs per SM are no faster (0.137 ms either way)
+#define YF_TCT_A_OCC 1
+#endif
+using CfgRes3aTt = IrbTtCfg<8, 48, 8, YF_TCT_A_TH, true, 0, YF_TCT_A_OCC>;
+using CfgWide3Tt = IrbTtCfg<8, 48, 16, YF_TCT_A_TH, false, 0, YF_TCT_A_OCC>;
 #ifndef YF_CFGRES4_TC
 #define YF_CFGRES4_TC IrbTcCfg<24, 136, 24, 8, 20, 32, 4, 10, true, true>
 #endif
@@ -569,7 +573,7 @@ void launch_irbt(const GroupArgs& g, const void*, bool, int B, cudaStream_t st, 
     if (tc->failed) return;
     const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
     const int total = B * tx * ty;
-    const int grid = total < g.nsm ? total : g.nsm;
+    const int grid = total < g.nsm * C::OCC ? total : g.nsm * C::OCC;
     irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.w + w_off, g.Hout, g.Wout, tx, ty, total);
 }
 template <class C>

@@ -62,8 +62,9 @@ __device__ __forceinline__ void tmem_ld_row10(uint32_t taddr, float (&v)[10]) {
 
 enum : int { TT_WORKER = 0, TT_EPI = 1, TT_STAGE = 2, TT_MMA = 3, TT_IDLE = 4 };
 
-template <int CIN_, int CMID_, int COUT_, int TH_, bool RES_, int TQ_ = 0>
+template <int CIN_, int CMID_, int COUT_, int TH_, bool RES_, int TQ_ = 0, int OCC_ = 1>
 struct IrbTtCfg {
+    static constexpr int OCC = OCC_;                                      // CTAs per SM (shared memory, TMEM columns and registers are sized for it)
     static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_;
     static constexpr bool RES = RES_;
     static constexpr int TH = TH_, TW = 8, OPIX = TH * TW;
@@ -89,7 +90,8 @@ struct IrbTtCfg {
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + 1024;
     // TMEM columns: two E buffers, then one or two O buffers
     static constexpr int EB = NMT * NPX, TM_O = 2 * EB;
-    static constexpr int NOB = (TM_O + 2 * 2 * COUTP <= 512) ? 2 : 1, TCOLS = 512;
+    static constexpr int TCOLS = 512 / OCC;
+    static constexpr int NOB = (TM_O + 2 * 2 * COUTP <= TCOLS) ? 2 : 1;
     static constexpr int NITEM = HPIX * (CIN / 4), NIT = cdiv(NITEM, NTA);       // staging items (halo pixel, 4 input channels) per tile / per staging thread
 
     // ---- roles. Worker warps of quarter q: G per M tile that has channels in that quarter.
@@ -127,12 +129,12 @@ struct IrbTtCfg {
     static_assert(CIN % 8 == 0 && COUT % 8 == 0 && NPX <= 256 && TM_O + NOB * 2 * COUTP <= TCOLS, "MMA shape / TMEM columns");
     static_assert(!RES || CIN == COUT, "residual needs same shape");
     static_assert((RAW * 4) % 128 == 0 && RAW < 65536 && XH < 65536, "raw box alignment / packed staging offsets");
-    static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
+    static_assert(OCC * (SMEM_BYTES + 1024) <= 227 * 1024 + 1024, "does not fit shared memory");
     static_assert(NT <= 1024, "too many warps");
 };
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, 1)
+__global__ void __launch_bounds__(C::NT, C::OCC)
 irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts,
             int H, int W, int tiles_x, int tiles_y, int total_tiles) {
     extern __shared__ unsigned char smem_raw[];
