@@ -290,7 +290,7 @@ using CfgRes3bTc = YF_CFGRES3B_TC;
 #ifndef YF_USE_TCT_A
 #define YF_USE_TCT_A 1  // 1: so do the 48-mid-channel groups res3_1, res3_2 and conv3_2 -> conv3_4
 #endif
-// IrbTtCfg<CIN, CMID, COUT, tile height (x 8 columns), RES, TMEM lane quarter of channel 128>
+// IrbTtCfg<CIN, CMID, COUT, tile height (x 8 columns), RES, TMEM lane quarter of channel 128, CTAs per SM, depthwise stride>
 using CfgRes3bTt = IrbTtCfg<16, 96, 16, 16, true>;
 using CfgRes4Tt = IrbTtCfg<24, 136, 24, 8, true, 2>;
 #ifndef YF_TCT_A_TH
@@ -299,6 +299,7 @@ using CfgRes4Tt = IrbTtCfg<24, 136, 24, 8, true, 2>;
 #endif
 using CfgRes3aTt = IrbTtCfg<8, 48, 8, YF_TCT_A_TH, true, 0, YF_TCT_A_OCC>;
 using CfgWide3Tt = IrbTtCfg<8, 48, 16, YF_TCT_A_TH, false, 0, YF_TCT_A_OCC>;
+using CfgDown3Tt = IrbTtCfg<16, 96, 24, 8, false, 0, 1, 2>;          // conv3_5 -> conv3_6 (stride 2) -> conv4_1
 #ifndef YF_CFGRES4_TC
 #define YF_CFGRES4_TC IrbTcCfg<24, 136, 24, 8, 20, 32, 4, 10, true, true>
 #endif
@@ -574,7 +575,7 @@ void launch_irbt(const GroupArgs& g, const void*, bool, int B, cudaStream_t st, 
     const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
     const int total = B * tx * ty;
     const int grid = total < g.nsm * C::OCC ? total : g.nsm * C::OCC;
-    irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.w + w_off, g.Hout, g.Wout, tx, ty, total);
+    irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.w + w_off, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
 }
 template <class C>
 cudaError_t init_irbt() { return cudaFuncSetAttribute(irbt_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
@@ -1237,7 +1238,12 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes3b>("res3_5", 16), 8, 8);
     chain(make_irb<CfgRes3b>("res3_6", 16), 8, 8);
 #endif
-    { Group g = make_irb<CfgDown3>("conv4_1", 24); g.launch = &launch_irb_auto<CfgDown3, CfgDown3N>; chain(g, 8, 16); }
+    {
+        Group g = make_irb<CfgDown3>("conv4_1", 24);
+        g.launch = &launch_irb_auto<CfgDown3, CfgDown3N>;
+        if (YF_USE_TC && YF_USE_TCT_A) { g.launch = &launch_irbt0<CfgDown3Tt>; g.occupancy = &occ_irbt<CfgDown3Tt>; }
+        chain(g, 8, 16);
+    }
 #if YF_USE_TC
     for (const char* n : {"res4_1", "res4_2", "res4_3", "res4_4"}) {
         Group g = make_irbtc<CfgRes4Tc>(n, 24);
@@ -1355,7 +1361,7 @@ extern "C" int yf_create_variant(yf_ctx** out, int device, int in_ch, int num_cl
         cudaFuncSetAttribute(post_kernel<YF_MODE_VALIDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         cudaFuncSetAttribute(post_kernel<POST_SRC_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbt<CfgRes3bTt>(), init_irbt<CfgRes4Tt>(), init_irbt<CfgRes3aTt>(), init_irbt<CfgWide3Tt>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbt<CfgRes3bTt>(), init_irbt<CfgRes4Tt>(), init_irbt<CfgRes3aTt>(), init_irbt<CfgWide3Tt>(), init_irbt<CfgDown3Tt>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -1441,7 +1447,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
 #else
     res(CfgRes3b{}, "res3_3"); res(CfgRes3b{}, "res3_4"); res(CfgRes3b{}, "res3_5"); res(CfgRes3b{}, "res3_6");
 #endif
-    offs.push_back(pack_irb<CfgDown3>(P, f, "conv3_5", "conv3_6", "conv4_1", "", 0));
+    offs.push_back((YF_USE_TC && YF_USE_TCT_A) ? pack_irbt<CfgDown3Tt>(P, f, "conv3_5", "conv3_6", "conv4_1") : pack_irb<CfgDown3>(P, f, "conv3_5", "conv3_6", "conv4_1", "", 0));
 #if YF_USE_TC
     for (const char* n : {"res4_1", "res4_2", "res4_3", "res4_4"})
     {

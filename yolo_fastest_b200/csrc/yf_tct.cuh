@@ -50,6 +50,20 @@ __device__ __forceinline__ void tmem_ld_row10(uint32_t taddr, float (&v)[10]) {
     for (int i = 0; i < 10; ++i) v[i] = fmaxf(__uint_as_float(r[i]), 0.f);
 }
 
+// the same for a stride-2 block: 17 columns per input row
+__device__ __forceinline__ void tmem_ld_row17(uint32_t taddr, float (&v)[17]) {
+    uint32_t r[17];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%16}, [%18];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16])
+        : "r"(taddr), "r"(taddr + 16) : "memory");
+#pragma unroll
+    for (int i = 0; i < 17; ++i) v[i] = fmaxf(__uint_as_float(r[i]), 0.f);
+}
+
 // -DYF_TC_TRACE -DYF_TCT_TRACE: CTA 0 records clock64() per tile: slots 0..4 worker warp 0, 6..9 tensor-core thread, 10..13 staging thread 0
 #if defined(YF_TC_TRACE) && defined(YF_TCT_TRACE)
 #ifndef YF_TCT_TRACE_CMID
@@ -62,15 +76,17 @@ __device__ __forceinline__ void tmem_ld_row10(uint32_t taddr, float (&v)[10]) {
 
 enum : int { TT_WORKER = 0, TT_EPI = 1, TT_STAGE = 2, TT_MMA = 3, TT_IDLE = 4 };
 
-template <int CIN_, int CMID_, int COUT_, int TH_, bool RES_, int TQ_ = 0, int OCC_ = 1>
+template <int CIN_, int CMID_, int COUT_, int TH_, bool RES_, int TQ_ = 0, int OCC_ = 1, int S_ = 1>
 struct IrbTtCfg {
+    static constexpr int S = S_;                                          // stride of the depthwise (2: the downsampling blocks, yolo_fastest.py:98-100)
     static constexpr int OCC = OCC_;                                      // CTAs per SM (shared memory, TMEM columns and registers are sized for it)
     static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_;
     static constexpr bool RES = RES_;
     static constexpr int TH = TH_, TW = 8, OPIX = TH * TW;
     static constexpr int G = TH / 4;                                      // groups of 4 output rows = worker warps per (M tile, quarter)
-    static constexpr int HR = TH + 2, HW = TW + 2, HPIX = HR * HW;        // halo tile, pixel n = r * HW + j
-    static constexpr int NPX = rup(HPIX, 16);                             // N of the expand MMA
+    static constexpr int HR = S * (TH - 1) + 3, HW = S * (TW - 1) + 3, HPIX = HR * HW;      // input halo tile, pixel n = r * HW + j
+    static constexpr int NSPL = cdiv(HPIX, 256);                          // expand MMAs per K block (N <= 256 each)
+    static constexpr int NPX = rup(HPIX, 16 * NSPL), NCH = NPX / NSPL;    // halo pixels incl. padding; N of one expand MMA
     static constexpr int KX = CIN + 8;                                    // + the ones channel (and 7 zero channels: K advances by 8)
     static constexpr int NMT = cdiv(CMID, 128);                           // M tiles of the expand GEMM
     // The second M tile's channels 128.. sit in TMEM lane quarter TQ.. of that tile (its A operand simply starts 32 TQ rows early, on
@@ -78,18 +94,19 @@ struct IrbTtCfg {
     static constexpr int TQ = TQ_;
     static constexpr int COUTP = rup(COUT, 16);
     static constexpr int NA = OPIX / 32, KB3 = NA * 256;                  // 32-pixel atoms / floats per 8-channel block of the operand D
-    static constexpr int NAUX = 2, NTA = NAUX * 32;                       // staging warps
+    static constexpr int NAUX = S == 2 ? 3 : 2, NTA = NAUX * 32;          // staging warps
     // packed weights
     static constexpr int W1ROWS = (NMT - 1) * 128 + rup(CMID - (NMT - 1) * 128, 8);
     static constexpr int OFF_W1H = 0, OFF_W1L = W1ROWS * KX, OFF_W2 = 2 * W1ROWS * KX, WRES = rup(OFF_W2 + 2 * COUTP * CMID, 256);
     static constexpr int OFF_WD = WRES, OFF_BD = OFF_WD + CMID * 9, OFF_B2 = OFF_BD + CMID, WFLOATS = rup(OFF_B2 + COUT, 32);
     // shared memory (floats)
     static constexpr int XH = NPX * KX, XL = NPX * CIN, DA = (CMID / 8) * KB3;
-    static constexpr int RW = 16, RAW = CIN * HR * RW;                    // raw input box [CIN][HR][RW] from column ox0 - 4 (TMA boxes start 16-byte aligned)
+    static constexpr int RW = rup(HW + 3, 4), RAW = CIN * HR * RW;        // raw input box [CIN][HR][RW] from column S ox0 - 4 (TMA boxes start 16-byte aligned)
     static constexpr int SMEM_FLOATS = WRES + 2 * DA + XH + XL + 2 * RAW;
     static constexpr int SMEM_BYTES = SMEM_FLOATS * 4 + 1024;
-    // TMEM columns: two E buffers, then one or two O buffers
-    static constexpr int EB = NMT * NPX, TM_O = 2 * EB;
+    // TMEM columns: one or two E buffers, then one or two O buffers
+    static constexpr int EB = NMT * NPX;
+    static constexpr int NEB = (2 * EB + 2 * COUTP <= 512 / OCC) ? 2 : 1, TM_O = NEB * EB;
     static constexpr int TCOLS = 512 / OCC;
     static constexpr int NOB = (TM_O + 2 * 2 * COUTP <= TCOLS) ? 2 : 1;
     static constexpr int NITEM = HPIX * (CIN / 4), NIT = cdiv(NITEM, NTA);       // staging items (halo pixel, 4 input channels) per tile / per staging thread
@@ -126,7 +143,8 @@ struct IrbTtCfg {
 
     static_assert(TH == 8 || TH == 16, "tile = 64 or 128 pixels");
     static_assert(CMID % 8 == 0 && NMT <= 2 && (TQ == 0 || NMT == 2) && TQ * 32 + CMID - 128 <= 128, "mid channels: whole 8-channel operand blocks, at most two M tiles");
-    static_assert(CIN % 8 == 0 && COUT % 8 == 0 && NPX <= 256 && TM_O + NOB * 2 * COUTP <= TCOLS, "MMA shape / TMEM columns");
+    static_assert(CIN % 8 == 0 && COUT % 8 == 0 && NCH % 16 == 0 && NCH <= 256 && TM_O + NOB * 2 * COUTP <= TCOLS, "MMA shape / TMEM columns");
+    static_assert((S == 1 || S == 2) && (S == 1 || !RES), "stride");
     static_assert(!RES || CIN == COUT, "residual needs same shape");
     static_assert((RAW * 4) % 128 == 0 && RAW < 65536 && XH < 65536, "raw box alignment / packed staging offsets");
     static_assert(OCC * (SMEM_BYTES + 1024) <= 227 * 1024 + 1024, "does not fit shared memory");
@@ -136,7 +154,7 @@ struct IrbTtCfg {
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::OCC)
 irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts,
-            int H, int W, int tiles_x, int tiles_y, int total_tiles) {
+            int Hin, int Win, int H, int W, int tiles_x, int tiles_y, int total_tiles) {
     extern __shared__ unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     float* Wr = base;                            // resident operands: W1hi | W1lo | W2
@@ -187,7 +205,7 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
     if (role == TT_MMA) {
         // ================= tensor-core warp =================
         if (ntile > 0 && elect_one()) {
-            constexpr uint32_t IDESC_E = umma_idesc_tf32(C::NPX) & ~(1u << 15);          // A and B K-major
+            constexpr uint32_t IDESC_E = umma_idesc_tf32(C::NCH) & ~(1u << 15);          // A and B K-major
             constexpr uint32_t IDESC3A = umma_idesc_tf32(2 * C::COUTP), IDESC3B = umma_idesc_tf32(C::COUTP);
             mbar_expect_tx(&wres, C::WRES * 4);
             bulk_load(Wr, wts, C::WRES * 4, &wres);
@@ -200,19 +218,24 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
             auto expand = [&](int t) {
 #pragma unroll
                 for (int mt = 0; mt < C::NMT; ++mt) {
-                    const uint32_t acc = tmem + (t & 1) * C::EB + mt * C::NPX;
                     const uint64_t mo = (uint64_t)((mt * (128 - 32 * C::TQ) * C::KX * 4) >> 4);   // this M tile's rows of W1
-                    // the two small correction terms first, the main term last: the tensor core accumulates with truncation, and every
-                    // add onto an accumulator that already holds the main term costs up to one ulp of it
 #pragma unroll
-                    for (int kb = 0; kb < C::CIN / 8; ++kb) umma_tf32(acc, dw1h + mo + (uint64_t)(kb * 16), dxl + (uint64_t)(kb * 16), IDESC_E, kb ? 1u : 0u);
+                    for (int ns = 0; ns < C::NSPL; ++ns) {
+                        const uint32_t acc = tmem + (t % C::NEB) * C::EB + mt * C::NPX + ns * C::NCH;
+                        const uint64_t xho = (uint64_t)(((ns * C::NCH / 8) * (C::KX / 4) * 128) >> 4);      // this chunk's pixels of X^T
+                        const uint64_t xlo = (uint64_t)(((ns * C::NCH / 8) * (C::CIN / 4) * 128) >> 4);
+                        // the two small correction terms first, the main term last: the tensor core accumulates with truncation, and every
+                        // add onto an accumulator that already holds the main term costs up to one ulp of it
 #pragma unroll
-                    for (int kb = 0; kb < C::KX / 8; ++kb) umma_tf32(acc, dw1l + mo + (uint64_t)(kb * 16), dxh + (uint64_t)(kb * 16), IDESC_E, 1u);
+                        for (int kb = 0; kb < C::CIN / 8; ++kb) umma_tf32(acc, dw1h + mo + (uint64_t)(kb * 16), dxl + xlo + (uint64_t)(kb * 16), IDESC_E, kb ? 1u : 0u);
 #pragma unroll
-                    for (int kb = 0; kb < C::KX / 8; ++kb) umma_tf32(acc, dw1h + mo + (uint64_t)(kb * 16), dxh + (uint64_t)(kb * 16), IDESC_E, 1u);
+                        for (int kb = 0; kb < C::KX / 8; ++kb) umma_tf32(acc, dw1l + mo + (uint64_t)(kb * 16), dxh + xho + (uint64_t)(kb * 16), IDESC_E, 1u);
+#pragma unroll
+                        for (int kb = 0; kb < C::KX / 8; ++kb) umma_tf32(acc, dw1h + mo + (uint64_t)(kb * 16), dxh + xho + (uint64_t)(kb * 16), IDESC_E, 1u);
+                    }
                 }
                 umma_commit(&xfree);
-                umma_commit(&efull[t & 1]);
+                umma_commit(&efull[t % C::NEB]);
             };
             auto project = [&](int t) {
                 const uint32_t acc = tmem + C::TM_O + (t % C::NOB) * 2 * C::COUTP;
@@ -232,7 +255,7 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
             for (int t = 0; t < ntile; ++t) {
                 if (t + 1 < ntile) {
                     mbar_wait(&xfull, (t + 1) & 1);
-                    if (t + 1 >= 2) mbar_wait(&efree[(t + 1) & 1], (((t + 1) >> 1) - 1) & 1);
+                    if (t + 1 >= C::NEB) mbar_wait(&efree[(t + 1) % C::NEB], (((t + 1) / C::NEB) - 1) & 1);
                     tc_fence_after();
                     TT_TRACE(t, 6);
                     expand(t + 1);
@@ -298,7 +321,7 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
             int b, oy0, ox0;
             origin(ti, b, oy0, ox0);
             mbar_expect_tx(&rawfull[ti & 1], C::RAW * 4);
-            tma_load4(Raw + (ti & 1) * C::RAW, &xmap, &rawfull[ti & 1], ox0 - 4, oy0 - 1, 0, b);
+            tma_load4(Raw + (ti & 1) * C::RAW, &xmap, &rawfull[ti & 1], C::S * ox0 - 4, C::S * oy0 - 1, 0, b);
         };
         if (ta == 0) {
             tma_prefetch_desc(&xmap);
@@ -329,8 +352,8 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
                     st4(xh, make_float4(hi[0], hi[1], hi[2], hi[3]));
                     st4(Xlo + (pl[i] & 0xFFFFu), make_float4(lo[0], lo[1], lo[2], lo[3]));
                     if (ta + i * C::NTA < C::HPIX) {           // channel group 0 also sets the ones channel: 1 inside the image (carries the expand bias)
-                        const int gy = oy0 - 1 + (int)((pl[i] >> 16) & 255u), gx = ox0 - 1 + (int)(pl[i] >> 24);
-                        const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+                        const int gy = C::S * oy0 - 1 + (int)((pl[i] >> 16) & 255u), gx = C::S * ox0 - 1 + (int)(pl[i] >> 24);
+                        const bool ok = (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win;
                         st4(xh + (C::CIN / 4) * 32, make_float4(ok ? 1.f : 0.f, 0.f, 0.f, 0.f));
                     }
                 }
@@ -359,29 +382,54 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
         float* dh = DAhi + (cl >> 3) * C::KB3 + rg * 256 + ((cl >> 2) & 1) * 128 + (cl & 3) * 32;
         float* dl = dh + C::DA;
         const bool swp = (cl >> 2) & 1;
-        const uint32_t te0 = tmem + ((uint32_t)(q * 32) << 16) + mt * C::NPX + (4 * rg) * C::HW;
+        const uint32_t te0 = tmem + ((uint32_t)(q * 32) << 16) + mt * C::NPX + (C::S * 4 * rg) * C::HW;
         for (int t = 0; t < ntile; ++t) {
-            const uint32_t te = te0 + (t & 1) * C::EB;
+            const uint32_t te = te0 + (t % C::NEB) * C::EB;
             if (tid == 0) TT_TRACE(t, 0);
-            mbar_wait(&efull[t & 1], (t >> 1) & 1);
+            mbar_wait(&efull[t % C::NEB], (t / C::NEB) & 1);
             tc_fence_after();
             if (tid == 0) TT_TRACE(t, 1);
-            float e[6][10], a[4][8];
+            float a[4][8];
+            if (C::S == 1) {
+                float e[6][10];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) tmem_ld_row10(te + r * C::HW, e[r]);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&efree[t & 1]);
+                for (int r = 0; r < 6; ++r) tmem_ld_row10(te + r * C::HW, e[r]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&efree[t % C::NEB]);
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
+                for (int rr = 0; rr < 4; ++rr) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[rr][i] = bd;
+                    for (int i = 0; i < 8; ++i) a[rr][i] = bd;
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
+                    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx)
+                        for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) a[rr][i] = fmaf(w[dy * 3 + dx], e[rr + dy][i + dx], a[rr][i]);
+                            for (int i = 0; i < 8; ++i) a[rr][i] = fmaf(w[dy * 3 + dx], e[rr + dy][i + dx], a[rr][i]);
+                }
+            } else {
+                // stride 2: output row rr reads input rows 2 rr .. 2 rr + 2 (17 columns each); three rows live at a time, row r in slot r % 3
+                float e[3][17];
+                tmem_ld_row17(te, e[0]);
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    tmem_ld_row17(te + (2 * rr + 1) * C::HW, e[(2 * rr + 1) % 3]);
+                    tmem_ld_row17(te + (2 * rr + 2) * C::HW, e[(2 * rr + 2) % 3]);
+                    if (rr == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&efree[t % C::NEB]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[rr][i] = bd;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) a[rr][i] = fmaf(w[dy * 3 + dx], e[(2 * rr + dy) % 3][2 * i + dx], a[rr][i]);
+                }
             }
             // everything above overlapped the project MMA of tile t - 1; only the operand stores have to wait for it
             if (tid == 0) TT_TRACE(t, 2);
