@@ -412,7 +412,7 @@ def main():
     # which engine runs a group decides the roof that binds it: the tcgen05 groups are contractions on the tensor pipe (bound
     # "tensor"), every other group runs on the FP32 CUDA cores and moves its activations once (bound = the larger of its HBM time and
     # its FP32 time; "hbm" for the thin 4-8 channel groups whose HBM time is the larger one)
-    TENSOR = {"conv2_1", "res3_1", "res3_2", "conv3_4", "res3_3", "res3_4", "res3_5", "res3_6", "conv4_1", "res4_1", "res4_2", "res4_3", "res4_4", "res5_1", "res5_2", "res5_3",
+    TENSOR = {"conv2_1", "res3_1", "res3_2", "conv3_4", "res3_3", "res3_4", "res3_5", "res3_6", "conv4_1", "res4_1", "res4_2", "res4_3", "res4_4", "conv5_1", "res5_1", "res5_2", "res5_3",
               "res5_4", "res5_5", "conv5_4", "head_5", "conv4_1_1", "conv4_1_3", "head_4"}
     bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
     tf32_peak = bf16_peak / 2.0                              # kind::tf32 issues at half the bf16 rate

@@ -6,5 +6,5 @@ echo "pytest exit $?"; tail -n 5 gpurun_out/pg3_pytest.log
 timeout 300 python tools/profile_groups.py 512x640 256 > gpurun_out/pg.json && python - <<'P'
 import json
 d=json.load(open("gpurun_out/pg.json")); g=d["groups"]
-print(d["total_ms"], d["err"], {k:g[k] for k in ("res3_1","conv3_4","res3_3","conv4_1","res4_1","conv5_1","conv2_1")})
+print(d["total_ms"], d["err"], {k:g[k] for k in ("res3_1","conv3_4","res3_3","conv4_1","res4_1","conv5_1","res5_1","conv4_1_1")})
 P

@@ -129,6 +129,7 @@ struct GroupArgs {
     float* y = nullptr;          // output activation (or head)
     float* skip = nullptr;       // dual output
     const float* w = nullptr;    // packed weights (device)
+    const float* w2 = nullptr;   // second weight block of the same group (the channel-lane kernel's, where a group keeps two engines)
     int Hin = 0, Win = 0, Hout = 0, Wout = 0;
     int headn = 0;
 };
@@ -290,7 +291,7 @@ using CfgRes3bTc = YF_CFGRES3B_TC;
 #ifndef YF_USE_TCT_A
 #define YF_USE_TCT_A 1  // 1: so do the 48-mid-channel groups res3_1, res3_2 and conv3_2 -> conv3_4
 #endif
-// IrbTtCfg<CIN, CMID, COUT, tile height (x 8 columns), RES, TMEM lane quarter of channel 128, CTAs per SM, depthwise stride>
+// IrbTtCfg<CIN, CMID, COUT, tile height (x 8 columns), RES, TMEM lane quarter of channel 128, CTAs per SM, depthwise stride, dual output, ReLU after the projection>
 using CfgRes3bTt = IrbTtCfg<16, 96, 16, 16, true>;
 using CfgRes4Tt = IrbTtCfg<24, 136, 24, 8, true, 2>;
 #ifndef YF_TCT_A_TH
@@ -300,13 +301,13 @@ using CfgRes4Tt = IrbTtCfg<24, 136, 24, 8, true, 2>;
 using CfgRes3aTt = IrbTtCfg<8, 48, 8, YF_TCT_A_TH, true, 0, YF_TCT_A_OCC>;
 using CfgWide3Tt = IrbTtCfg<8, 48, 16, YF_TCT_A_TH, false, 0, YF_TCT_A_OCC>;
 using CfgDown3Tt = IrbTtCfg<16, 96, 24, 8, false, 0, 1, 2>;          // conv3_5 -> conv3_6 (stride 2) -> conv4_1
+using CfgDown4Tt = IrbTtCfg<24, 136, 48, 4, false, 1, 1, 2, true, true>;    // conv4_2 (also the neck's skip tensor) -> conv4_3 (stride 2) -> conv5_1
 #ifndef YF_CFGRES4_TC
 #define YF_CFGRES4_TC IrbTcCfg<24, 136, 24, 8, 20, 32, 4, 10, true, true>
 #endif
 using CfgRes4Tc = YF_CFGRES4_TC;
 // res4 maps are 1/16 of the input: their rows are a multiple of 16 bytes (what a TMA tensor map needs) only when the input width is a
-// multiple of 64. Other widths (416 -> 26 columns) keep the pixel-lane kernel; both weight blocks sit in the group's blob.
-constexpr int64_t RES4_TT_OFF = (CfgRes4Tc::WFLOATS + 31) / 32 * 32;
+// multiple of 64. Other widths (416 -> 26 columns) keep the pixel-lane kernel; the group holds both weight blocks (GroupArgs::w, w2).
 #ifndef YF_USE_TC
 #define YF_USE_TC 1     // 1: res3_3..6 and res4_1..4 run on the tcgen05 kernel (yf_tc.cuh); 0: everything on the FFMA engine (libyf_b200_ffma.so)
 #endif
@@ -575,7 +576,7 @@ void launch_irbt(const GroupArgs& g, const void*, bool, int B, cudaStream_t st, 
     const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
     const int total = B * tx * ty;
     const int grid = total < g.nsm * C::OCC ? total : g.nsm * C::OCC;
-    irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.w + w_off, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
+    irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.skip, g.w + w_off, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
 }
 template <class C>
 cudaError_t init_irbt() { return cudaFuncSetAttribute(irbt_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
@@ -583,8 +584,14 @@ template <class C> void launch_irbt0(const GroupArgs& g, const void* x, bool u8,
 // res4: the channel-lane kernel where the map's rows can be a TMA tensor (shape only: the choice never depends on the batch)
 template <class CT, class CB, class CS, class CXS>
 void launch_res4_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
-    if (g.Wout % 4 == 0) launch_irbt<CT>(g, x, u8, B, st, RES4_TT_OFF);
+    if (g.Wout % 4 == 0) launch_irbt<CT>(g, x, u8, B, st, g.w2 - g.w);
     else launch_irbtc_auto<CB, CS, CXS>(g, x, u8, B, st);
+}
+// conv5_1's input is a 1/16 map as well: same rule, same two weight blocks
+template <class CT, class CB, class CN>
+void launch_down4_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {
+    if (g.Win % 4 == 0) launch_irbt<CT>(g, x, u8, B, st, g.w2 - g.w);
+    else launch_irb_auto<CB, CN>(g, x, u8, B, st);
 }
 template <class C> int occ_irbt() { return occ_of(irbt_kernel<C>, C::NT, C::SMEM_BYTES); }
 template <class C> int occ_irbtc() { return occ_of(irbtc_kernel<C>, C::NT, C::SMEM_BYTES); }
@@ -1263,6 +1270,7 @@ static void build_plan(yf_ctx* ctx) {
     {
         Group g = make_irb<CfgDown4>("conv5_1", 48);
         g.launch = &launch_irb_auto<CfgDown4, CfgDown4N>;
+        if (YF_USE_TC && YF_USE_TCT_A) g.launch = &launch_down4_auto<CfgDown4Tt, CfgDown4, CfgDown4N>;
         g.a.skip = ctx->d_skip;
         chain(g, 16, 32);
     }
@@ -1361,7 +1369,7 @@ extern "C" int yf_create_variant(yf_ctx** out, int device, int in_ch, int num_cl
         cudaFuncSetAttribute(post_kernel<YF_MODE_VALIDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         cudaFuncSetAttribute(post_kernel<POST_SRC_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12),
         init_irb<CfgRes2>(), init_irb<CfgDown2>(), init_irb<CfgRes3a>(), init_irb<CfgWide3>(),
-        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbt<CfgRes3bTt>(), init_irbt<CfgRes4Tt>(), init_irbt<CfgRes3aTt>(), init_irbt<CfgWide3Tt>(), init_irbt<CfgDown3Tt>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
+        init_irb<CfgRes3b>(), init_irbtc<CfgRes3bTc>(), init_irbt<CfgRes3bTt>(), init_irbt<CfgRes4Tt>(), init_irbt<CfgRes3aTt>(), init_irbt<CfgWide3Tt>(), init_irbt<CfgDown3Tt>(), init_irbt<CfgDown4Tt>(), init_irbtc<CfgRes4Tc>(), init_irbtc2<CfgRes5Tc>(), init_irbtc2<CfgRes5TcS>(), init_irbtc2<CfgRes5TcXS>(), init_irbtc2<CfgRes5TcN>(), init_dwpwtc<CfgNeckS1TcS>(), init_dwpwtc<CfgNeckS2TcS>(), init_irbtc<CfgRes3bTcXS>(), init_irbtc<CfgRes4TcXS>(), init_dwpwtc<CfgNeckS1TcN>(), init_dwpwtc<CfgNeckS2TcN>(), init_dwpwtc<CfgNeckL1TcN>(), init_dwpwtc<CfgNeckL2TcN>(), init_irb<CfgDown3N>(), init_irb<CfgDown4N>(), init_dwpwtc<CfgNeckL1TcS>(), init_dwpwtc<CfgNeckL2TcS>(), init_irbtc<CfgRes3bTcS>(), init_irbtc<CfgRes4TcS>(), init_dwpwtc<CfgNeckS1Tc>(), init_dwpwtc<CfgNeckL1Tc>(), init_dwpwtc<CfgNeckS2Tc>(), init_dwpwtc<CfgNeckL2Tc>(), init_irb<CfgDown3>(), init_irb<CfgRes4>(), init_irb<CfgDown4>(), init_irb<CfgRes5>(),
         init_irb<CfgNeckS1>(), init_irb<CfgNeckS2>(), init_irb<CfgNeckL1>(), init_irb<CfgNeckL2>()};
     for (cudaError_t x : ie)
         if (x != cudaSuccess) { set_err(&ctx->err, "cudaFuncSetAttribute: %s", cudaGetErrorString(x)); return fail(YF_ERR_CUDA); }
@@ -1414,6 +1422,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     std::vector<float>& P = ctx->host_packed;
     P.clear();
     std::vector<int64_t> offs;
+    std::map<size_t, int64_t> offs2;                 // group index -> offset of its second weight block
     auto res = [&](auto tag, const std::string& n) {
         using C = decltype(tag);
         offs.push_back(pack_irb<C>(P, f, n + ".conv1", n + ".conv2", n + ".conv3", "", 0));
@@ -1452,13 +1461,13 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     for (const char* n : {"res4_1", "res4_2", "res4_3", "res4_4"})
     {
         offs.push_back(pack_irbtc<CfgRes4Tc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
-        if (YF_USE_TCT && pack_irbt<CfgRes4Tt>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3") != offs.back() + RES4_TT_OFF)
-            { set_err(&ctx->err, "internal: res4 weight blocks at an unexpected offset"); return YF_ERR_STATE; }
+        if (YF_USE_TCT) offs2[offs.size() - 1] = pack_irbt<CfgRes4Tt>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3");
     }
 #else
     res(CfgRes4{}, "res4_1"); res(CfgRes4{}, "res4_2"); res(CfgRes4{}, "res4_3"); res(CfgRes4{}, "res4_4");
 #endif
     offs.push_back(pack_irb<CfgDown4>(P, f, "conv4_2", "conv4_3", "conv5_1", "", 0));
+    if (YF_USE_TC && YF_USE_TCT_A) offs2[offs.size() - 1] = pack_irbt<CfgDown4Tt>(P, f, "conv4_2", "conv4_3", "conv5_1");
 #if YF_RES5_TC
     for (const char* n : {"res5_1", "res5_2", "res5_3", "res5_4", "res5_5"})
         offs.push_back(pack_irbtc2<CfgRes5Tc>(P, f, std::string(n) + ".conv1", std::string(n) + ".conv2", std::string(n) + ".conv3"));
@@ -1492,6 +1501,7 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     CU(cudaMalloc(&ctx->d_w, sizeof(float) * P.size()));
     CU(cudaMemcpy(ctx->d_w, P.data(), sizeof(float) * P.size(), cudaMemcpyHostToDevice));
     for (size_t i = 0; i < offs.size(); ++i) { ctx->groups[i].w_off = offs[i]; ctx->groups[i].a.w = ctx->d_w + offs[i]; }
+    for (const auto& kv : offs2) ctx->groups[kv.first].a.w2 = ctx->d_w + kv.second;
     ctx->weights_loaded = true;
     return YF_OK;
 }

@@ -50,6 +50,8 @@ __device__ __forceinline__ void tmem_ld_row10(uint32_t taddr, float (&v)[10]) {
     for (int i = 0; i < 10; ++i) v[i] = fmaxf(__uint_as_float(r[i]), 0.f);
 }
 
+__device__ __forceinline__ void st4g(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
 // the same for a stride-2 block: 17 columns per input row
 __device__ __forceinline__ void tmem_ld_row17(uint32_t taddr, float (&v)[17]) {
     uint32_t r[17];
@@ -76,8 +78,10 @@ __device__ __forceinline__ void tmem_ld_row17(uint32_t taddr, float (&v)[17]) {
 
 enum : int { TT_WORKER = 0, TT_EPI = 1, TT_STAGE = 2, TT_MMA = 3, TT_IDLE = 4 };
 
-template <int CIN_, int CMID_, int COUT_, int TH_, bool RES_, int TQ_ = 0, int OCC_ = 1, int S_ = 1>
+template <int CIN_, int CMID_, int COUT_, int TH_, bool RES_, int TQ_ = 0, int OCC_ = 1, int S_ = 1, bool SKIP_ = false, bool RELU_OUT_ = false>
 struct IrbTtCfg {
+    static constexpr bool RELU_OUT = RELU_OUT_;                           // ReLU after the projection (conv5_1 is a conv_norm_relu, yolo_fastest.py:124)
+    static constexpr bool SKIP = SKIP_;                                   // also write relu(expand) to HBM (conv4_2, the neck's skip tensor; stride-2 blocks only)
     static constexpr int S = S_;                                          // stride of the depthwise (2: the downsampling blocks, yolo_fastest.py:98-100)
     static constexpr int OCC = OCC_;                                      // CTAs per SM (shared memory, TMEM columns and registers are sized for it)
     static constexpr int CIN = CIN_, CMID = CMID_, COUT = COUT_;
@@ -141,7 +145,8 @@ struct IrbTtCfg {
     }
     static constexpr int NWARP = nwarp(), NT = NWARP * 32;
 
-    static_assert(TH == 8 || TH == 16, "tile = 64 or 128 pixels");
+    static_assert(TH == 4 || TH == 8 || TH == 16, "tile = 32, 64 or 128 pixels");
+    static_assert(!SKIP || S == 2, "the dual output is written by the stride-2 worker loop");
     static_assert(CMID % 8 == 0 && NMT <= 2 && (TQ == 0 || NMT == 2) && TQ * 32 + CMID - 128 <= 128, "mid channels: whole 8-channel operand blocks, at most two M tiles");
     static_assert(CIN % 8 == 0 && COUT % 8 == 0 && NCH % 16 == 0 && NCH <= 256 && TM_O + NOB * 2 * COUTP <= TCOLS, "MMA shape / TMEM columns");
     static_assert((S == 1 || S == 2) && (S == 1 || !RES), "stride");
@@ -153,7 +158,7 @@ struct IrbTtCfg {
 
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::OCC)
-irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ wts,
+irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ x, float* __restrict__ y, float* __restrict__ skip, const float* __restrict__ wts,
             int Hin, int Win, int H, int W, int tiles_x, int tiles_y, int total_tiles) {
     extern __shared__ unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -300,7 +305,7 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
             if (lane == 0) mbar_arrive(&ofree[ob]);
             if (ok) {
 #pragma unroll
-                for (int i = 0; i < C::COUT; ++i) y[off + i * plane] = r[i];
+                for (int i = 0; i < C::COUT; ++i) y[off + i * plane] = C::RELU_OUT ? fmaxf(r[i], 0.f) : r[i];
             }
         }
     } else if (role == TT_STAGE) {
@@ -412,10 +417,27 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
                 // stride 2: output row rr reads input rows 2 rr .. 2 rr + 2 (17 columns each); three rows live at a time, row r in slot r % 3
                 float e[3][17];
                 tmem_ld_row17(te, e[0]);
+                int sb = 0, soy0 = 0, sox0 = 0;
+                if (C::SKIP) origin(t, sb, soy0, sox0);
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                     tmem_ld_row17(te + (2 * rr + 1) * C::HW, e[(2 * rr + 1) % 3]);
                     tmem_ld_row17(te + (2 * rr + 2) * C::HW, e[(2 * rr + 2) % 3]);
+                    if (C::SKIP) {
+                        // input rows 1..8 and columns 1..16 of the halo tile are the pixels this tile OWNS (each input pixel is owned by
+                        // exactly one tile): relu(expand) of this thread's channel goes out as 64-byte row segments
+#pragma unroll
+                        for (int k = 1; k <= 2; ++k) {
+                            const int r = 2 * rr + k, gy = 2 * (soy0 + 4 * rg) - 1 + r;
+                            if (cvalid && gy < Hin) {
+                                float* sp = skip + (((size_t)sb * C::CMID + c) * Hin + gy) * Win + 2 * sox0;
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4)
+                                    if (2 * sox0 + 4 * j4 < Win)
+                                        st4g(sp + 4 * j4, make_float4(e[r % 3][1 + 4 * j4], e[r % 3][2 + 4 * j4], e[r % 3][3 + 4 * j4], e[r % 3][4 + 4 * j4]));
+                            }
+                        }
+                    }
                     if (rr == 3) {
                         tc_fence_before();
                         __syncwarp();
