@@ -947,7 +947,7 @@ int64_t pack_stem(std::vector<float>& out, const Folded& f) {
     return off;
 }
 
-// dense_tc_kernel: 27 resident B operands (channel block cb, tap t): 64 rows x 8 input channels, rows 0..23 = hi, 32..55 = lo of W9
+// dense_tc_kernel: 27 resident B operands (channel block cb, tap t): 64 rows x 8 input channels, rows 0..23 = hi, 24..47 = lo of W9
 int64_t pack_dense_tc(std::vector<float>& out, const Folded& f) {
     using C = CfgDenseTc;
     pad4(out);
@@ -960,7 +960,7 @@ int64_t pack_dense_tc(std::vector<float>& out, const Folded& f) {
         for (int t = 0; t < 9; ++t) {
             float* blk = o + (int64_t)(cb * 9 + t) * 512;
             for (int n = 0; n < 24; ++n)
-                for (int kl = 0; kl < 8; ++kl) put_kmajor_split(blk, blk + 32 * 8, n, kl, 8, w9[((n * 24 + cb * 8 + kl) * 3 + t / 3) * 3 + t % 3]);
+                for (int kl = 0; kl < 8; ++kl) put_kmajor_split(blk, blk + 24 * 8, n, kl, 8, w9[((n * 24 + cb * 8 + kl) * 3 + t / 3) * 3 + t % 3]);
         }
     for (int c = 0; c < 24; ++c)                                                // [24][4] -> [c / 4][k][c % 4]: one 128-bit load = 4 channels of one k
         for (int k = 0; k < 4; ++k) o[C::OFF_W8 + (c / 4) * 16 + k * 4 + (c % 4)] = f.w("conv1_8")[c * 4 + k];

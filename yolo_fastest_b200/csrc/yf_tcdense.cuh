@@ -13,11 +13,13 @@
 // therefore copied every tap into its own operand block — 2.25 stores per E value, 21 k instructions per tile — and was worker-bound.)
 //
 // One step = one block of 8 channels (2 channel groups) of E for the whole input tile, 3 steps per tile, 3-deep ring; per step the
-// tensor-core thread issues 9 taps x { E_hi . [W9hi | W9lo] (N = 64), E_lo . W9hi (N = 32, into the correction columns) } into
+// tensor-core thread issues 9 taps x { E_hi . [W9hi | W9lo] (N = 48), E_lo . W9hi (N = 32, into the correction columns) } into
 // the step's own accumulator (chains of 9 MMAs: the tensor core accumulates with truncation); all 27 weight blocks (55 KB) are
 // resident. The accumulators of a tile are double buffered in TMEM, so the epilogue of tile t (thread = pixel: sum of the three
 // accumulators + b9, ReLU, then conv2_1 as FMAs in registers) runs one step late and overlaps the MMAs of tile t + 1.
-// Packed weights (floats): [27 x (64 x 8 K-major): rows 0..23 W9hi, 32..55 W9lo][w8: 24 x 4][b8: 24][b9: 24][w21 transposed: 24 x 8][b21: 8].
+// tcgen05 dispatch floor (128 N / 256 cycles per K = 8 MMA): 27 x (24 + 16) = 1080 cycles per tile, a fifth of the ~5.1 k cycles a tile
+// takes — the kernel is bound by its producer warps, not by the pipe.
+// Packed weights (floats): [27 x (64 x 8 K-major): rows 0..23 W9hi, 24..47 W9lo][w8: 24 x 4][b8: 24][b9: 24][w21 transposed: 24 x 8][b21: 8].
 #pragma once
 #include "yf_tcpw.cuh"
 
@@ -54,7 +56,8 @@ struct DenseTcCfg {
     static constexpr int OFF_W8 = WRES, OFF_B8 = OFF_W8 + 96, OFF_B9 = OFF_B8 + 24, OFF_W21 = OFF_B9 + 24, OFF_B21 = OFF_W21 + 192;   // all multiples of 4
     static constexpr int WFLOATS = rup(OFF_B21 + 8, 4);
     static constexpr int WPAD = rup(WFLOATS, 32);
-    static constexpr int TCOLS = 512;                                               // 2 tile buffers x (3 step accumulators x 64 + 32 correction columns)
+    static constexpr int NMAIN = 48, OBUF = 3 * NMAIN + 32;                         // columns of a step accumulator (hi.hi | hi.lo) / of a tile buffer
+    static constexpr int TCOLS = 512;                                               // 2 tile buffers x (3 step accumulators x 48 + 32 correction columns)
     static constexpr int NPIX_IN = RH * RW;
     static constexpr int NTH = NTW / 2, IPT = cdiv(NPIX_IN, NTH);                   // half of the workers per channel group; input pixels per thread and step
     static constexpr int NSTG = 4 * RH * XWP, SPT = cdiv(NSTG, NTW);                // x-tile staging copies (8 bytes each) per tile / per producer thread
@@ -98,7 +101,7 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
         // ================= tensor-core warp =================
         if (ntile > 0 && elect_one()) {
             // instruction descriptors: A is K-major here (bit 15 clear), unlike the MN-major operands of the other kernels
-            constexpr uint32_t IDESC_A = umma_idesc_tf32(64) & ~(1u << 15), IDESC_B = umma_idesc_tf32(32) & ~(1u << 15);
+            constexpr uint32_t IDESC_A = umma_idesc_tf32(C::NMAIN) & ~(1u << 15), IDESC_B = umma_idesc_tf32(32) & ~(1u << 15);
             mbar_expect_tx(&wres, C::WFLOATS * 4);
             bulk_load(Wr, wts, C::WFLOATS * 4, &wres);
             // A: core matrices of 8 pixels x 16 B; K-adjacent one = next channel group (2 planes further, LBO), next row group = two input rows (SBO)
@@ -117,10 +120,10 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
                     DTRACE(ti, 8 + cb);
                     const uint64_t db = de0 + (uint64_t)(((uint32_t)sl * C::SLOT * 4) >> 4);
                     // two independent accumulation chains, interleaved so consecutive MMAs never wait for each other's accumulator:
-                    //   main  (one per step, 9 MMAs): E_hi . [W9hi | W9lo]  -> columns cb * 64 + [0, 64)
-                    //   corr  (one per tile, 27 MMAs): E_lo . W9hi          -> columns 192 + [0, 32)
+                    //   main  (one per step, 9 MMAs): E_hi . [W9hi | W9lo]  -> columns cb * 48 + [0, 48)
+                    //   corr  (one per tile, 27 MMAs): E_lo . W9hi          -> columns 144 + [0, 32)
                     // (the tensor core accumulates with truncation: the main term gets the short chain, the small correction the long one)
-                    const uint32_t acc = tmem + ob * 224 + cb * 64, corr = tmem + ob * 224 + 192;
+                    const uint32_t acc = tmem + ob * C::OBUF + cb * C::NMAIN, corr = tmem + ob * C::OBUF + 3 * C::NMAIN;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int ky = t / 3, kx = t % 3;
@@ -156,24 +159,27 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
                 const int ob = ti & 1;
                 mbar_wait(&ofull[ob], (ti >> 1) & 1);
                 tc_fence_after();
-                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + ob * 224;
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + ob * C::OBUF;
                 if (em == 0) DTRACE(ti, 5);
                 float v[24];
                 {
                     uint32_t c[32];
-                    tmem_ld32(ta + 192, c);                                          // the tile's lo . hi correction accumulator
+                    tmem_ld32(ta + 3 * C::NMAIN, c);                                          // the tile's lo . hi correction accumulator
 #pragma unroll
                     for (int n = 0; n < 24; ++n) v[n] = __uint_as_float(c[n]) + Wr[C::OFF_B9 + n];
                 }
 #pragma unroll
                 for (int cb = 0; cb < 3; ++cb) {
+                    uint32_t a[32];
+                    float a2[16];                                          // columns [0, 24) E_hi . W9hi, [24, 48) E_hi . W9lo
+                    tmem_ld32(ta + cb * C::NMAIN, a);
+                    tmem_ld16(ta + cb * C::NMAIN + 32, a2);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {                                    // E_hi . W9hi, then E_hi . W9lo
-                        uint32_t a[32];
-                        tmem_ld32(ta + cb * 64 + h * 32, a);
+                    for (int n = 0; n < 24; ++n) v[n] += __uint_as_float(a[n]);
 #pragma unroll
-                        for (int n = 0; n < 24; ++n) v[n] += __uint_as_float(a[n]);
-                    }
+                    for (int n = 0; n < 8; ++n) v[n] += __uint_as_float(a[24 + n]);
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) v[8 + n] += a2[n];
                 }
                 tc_fence_before();
                 __syncwarp();

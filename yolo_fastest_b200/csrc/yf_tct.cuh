@@ -71,7 +71,10 @@ __device__ __forceinline__ void tmem_ld_row17(uint32_t taddr, float (&v)[17]) {
 #ifndef YF_TCT_TRACE_CMID
 #define YF_TCT_TRACE_CMID 96
 #endif
-#define TT_TRACE(tile, ev) do { if (C::CMID == YF_TCT_TRACE_CMID && blockIdx.x == 0 && (tile) < 64) g_tc_trace[(tile) * 16 + (ev)] = clock64(); } while (0)
+#ifndef YF_TCT_TRACE_S
+#define YF_TCT_TRACE_S 1
+#endif
+#define TT_TRACE(tile, ev) do { if (C::CMID == YF_TCT_TRACE_CMID && C::S == YF_TCT_TRACE_S && blockIdx.x == 0 && (tile) < 64) g_tc_trace[(tile) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define TT_TRACE(tile, ev) do { } while (0)
 #endif
