@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/yf.h"
@@ -130,9 +131,24 @@ struct GroupArgs {
     float* skip = nullptr;       // dual output
     const float* w = nullptr;    // packed weights (device)
     const float* w2 = nullptr;   // second weight block of the same group (the channel-lane kernel's, where a group keeps two engines)
+    bool pdl = false;            // launch with programmatic stream serialization (set per launch by forward_impl; kernels with pdl_wait() only)
     int Hin = 0, Win = 0, Hout = 0, Wout = 0;
     int headn = 0;
 };
+
+// Launch with (pdl) or without the programmatic-stream-serialization attribute (yf_kernels.cuh: pdl_wait). Only kernels that execute
+// pdl_wait() before their first activation access may be launched with it.
+template <class... KA, class... A>
+inline void launch_k(bool pdl, void (*kernel)(KA...), int grid, int block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
 
 struct Group {
     int (*occupancy)() = nullptr;                       // resident CTAs per SM of the group's kernel (persistent groups)
@@ -177,6 +193,7 @@ struct yf_ctx {
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_back = nullptr;      // H2D of inputs / kernels / D2H of results
     cudaStream_t s_cap = nullptr;                       // graphs are captured here (the caller's stream may be the legacy stream, which cannot capture)
     cudaStream_t s_side = nullptr;                      // small batches: the head_5 branch runs here, beside the upsample branch
+    bool last_forward_forked = false;                   // the last forward ended with an event join: the head kernel is launched the ordinary way
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned char* sl_u8[2] = {nullptr, nullptr};
     yf_det* sl_out[2] = {nullptr, nullptr};
@@ -444,7 +461,7 @@ void launch_upcat_tc(const GroupArgs& g, const void*, bool, int B, cudaStream_t 
     const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;
-    upcat_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.x2, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+    launch_k(g.pdl, upcat_tc_kernel<C>, grid, C::NT, C::SMEM_BYTES, st, g.x, g.x2, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
 }
 
 // warp-streaming groups: one warp per (image, band of R output rows, strip of OW columns). The band height is chosen per launch:
@@ -477,7 +494,7 @@ void launch_wirb(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) 
     const int nstrips = cdiv(g.Wout, C::OW), nbands = cdiv(g.Hout, R);
     const int total = B * nstrips * nbands;
     const int grid = std::min(g.nsm, cdiv(total, C::NW));
-    wirb_kernel<C><<<grid, C::NW * 32, C::SMEM_BYTES, st>>>(tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
+    launch_k(g.pdl, wirb_kernel<C>, grid, C::NW * 32, C::SMEM_BYTES, st, tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
 }
 // stem group on the warp-streaming engine (single-channel input): the raw image is the TMA tensor, fp32 or uint8
 template <class C>
@@ -494,8 +511,8 @@ void launch_wstem(const GroupArgs& g, const void* xin, bool u8in, int B, cudaStr
     const int nstrips = cdiv(g.Wout, C::OW), nbands = cdiv(g.Hout, R);
     const int total = B * nstrips * nbands;
     const int grid = std::min(g.nsm, cdiv(total, C::NW));
-    if (u8in) wstem_kernel<C, true><<<grid, C::NW * 32, C::template smem_bytes<true>(), st>>>(tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
-    else wstem_kernel<C, false><<<grid, C::NW * 32, C::template smem_bytes<false>(), st>>>(tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
+    if (u8in) launch_k(g.pdl, wstem_kernel<C, true>, grid, C::NW * 32, C::template smem_bytes<true>(), st, tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
+    else launch_k(g.pdl, wstem_kernel<C, false>, grid, C::NW * 32, C::template smem_bytes<false>(), st, tc->map, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, R, nstrips, nbands, total);
 }
 template <class C>
 cudaError_t init_wstem() {
@@ -513,7 +530,7 @@ void launch_dwpwtc(const GroupArgs& g, const void*, bool, int B, cudaStream_t st
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;
-    dwpw_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total, g.headn > 0 ? g.headn : C::N);
+    launch_k(g.pdl, dwpw_tc_kernel<C>, grid, C::NT, C::SMEM_BYTES, st, g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total, g.headn > 0 ? g.headn : C::N);
 }
 template <class CB, class CS, class CN>
 void launch_dwpwtc_auto(const GroupArgs& g, const void* x, bool u8, int B, cudaStream_t st) {      // CS: small batches, CN: narrow maps
@@ -533,7 +550,7 @@ void launch_irbtc2(const GroupArgs& g, const void*, bool, int B, cudaStream_t st
     const int tx = cdiv(g.Wout, G::TW), ty = cdiv(g.Hout, G::TH);
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;
-    irbtc2_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
+    launch_k(g.pdl, irbtc2_kernel<C>, grid, C::NT, C::SMEM_BYTES, st, g.x, g.y, g.w, g.Hout, g.Wout, tx, ty, total);
 }
 // big tiles unless they would occupy less than half of the SMs (small batches): then the half-height variant
 template <class CB, class CS>
@@ -576,7 +593,7 @@ void launch_irbt(const GroupArgs& g, const void*, bool, int B, cudaStream_t st, 
     const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
     const int total = B * tx * ty;
     const int grid = total < g.nsm * C::OCC ? total : g.nsm * C::OCC;
-    irbt_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(tc->map, g.x, g.y, g.skip, g.w + w_off, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
+    launch_k(g.pdl, irbt_kernel<C>, grid, C::NT, C::SMEM_BYTES, st, tc->map, g.x, g.y, g.skip, g.w + w_off, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
 }
 template <class C>
 cudaError_t init_irbt() { return cudaFuncSetAttribute(irbt_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); }
@@ -616,7 +633,7 @@ void launch_dense_tc(const GroupArgs& g, const void*, bool, int B, cudaStream_t 
     const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;
-    dense_tc_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
+    launch_k(g.pdl, dense_tc_kernel<C>, grid, C::NT, C::SMEM_BYTES, st, g.x, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
 }
 void launch_dense(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using C = CfgDense;
@@ -630,7 +647,7 @@ void launch_pw52(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) 
     using C = CfgPw52;
     const int HW = g.Hin * g.Win;
     const int tiles = cdiv(HW, C::PIXT);
-    pw_kernel<C><<<B * tiles, C::NT, C::SMEM_BYTES, st>>>(g.x, g.y, g.w, HW, tiles);
+    launch_k(g.pdl, pw_kernel<C>, B * tiles, C::NT, C::SMEM_BYTES, st, g.x, g.y, g.w, HW, tiles);
 }
 void launch_lite34(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using C = CfgLite34;
@@ -1509,6 +1526,13 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch pays where the launches are latency chains: measured (tools/pdl_ab.sh, profiles/r02_pdl_ab.txt) 0.369 -> 0.329 ms
+// per batch-1 yf_detect on a stream, nothing inside a replayed CUDA graph (no launch gaps to hide), and -1.3% at batch 256 (the next
+// kernel's CTAs take the slots of the finishing ones early and then only wait). So: small batches only. YF_PDL_MAX overrides (0 = never).
+static bool pdl_enabled(int B) {
+    static const int pdl_max = getenv("YF_PDL_MAX") ? atoi(getenv("YF_PDL_MAX")) : 16;
+    return B <= pdl_max;
+}
 static const int kForkMaxBatch = 128;   // measured: -9% at batch 1, -2% at 64, -1% at 128, neutral at 256
 static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* head_large, float* head_small, cudaStream_t st) {
     if (!ctx->weights_loaded) { set_err(&ctx->err, "yf_load_weights has not been called"); return YF_ERR_STATE; }
@@ -1535,6 +1559,7 @@ static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* hea
             CU(cudaEventRecord(ctx->ev_fork, st));
             CU(cudaStreamWaitEvent(ctx->s_side, ctx->ev_fork, 0));
         }
+        a.pdl = pdl_enabled(B) && !(side && !h5);          // not behind an event wait (the first launch of the side stream)
         g.launch(a, x, u8in, B, side ? ctx->s_side : st);
         if (side && h5) CU(cudaEventRecord(ctx->ev_join, ctx->s_side));
         ctx->launches++;
@@ -1548,6 +1573,7 @@ static int forward_impl(yf_ctx* ctx, const void* x, bool u8in, int B, float* hea
         }
     }
     if (fork) CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    ctx->last_forward_forked = fork;
     CU(cudaGetLastError());
     for (Group& g : ctx->groups)
         if (g.tcache.failed) { set_err(&ctx->err, "cuTensorMapEncodeTiled failed for group '%s'", g.name); g.tcache.ptr = nullptr; return YF_ERR_CUDA; }
@@ -1652,8 +1678,10 @@ static int post_impl(yf_ctx* ctx, const float* hl, const float* hs, int B, int h
     a.NC = NC;
     a.rec = ctx->p_rec; a.conf = ctx->p_conf; a.cls = ctx->p_cls; a.sbox = ctx->p_sbox; a.order = ctx->p_order; a.alive = ctx->p_alive;
     a.sort_cap = post_sort_cap(NC);
-    if (p->mode == YF_MODE_DETECT) post_kernel<YF_MODE_DETECT><<<B, POST_NT, a.sort_cap * 12, st>>>(a);
-    else post_kernel<YF_MODE_VALIDATE><<<B, POST_NT, a.sort_cap * 12, st>>>(a);
+    // programmatic launch behind the last forward kernel of this stream, unless the forward forked (the join is an event dependency)
+    const bool pdl = pdl_enabled(B) && !ctx->last_forward_forked;
+    if (p->mode == YF_MODE_DETECT) launch_k(pdl, post_kernel<YF_MODE_DETECT>, B, POST_NT, (size_t)a.sort_cap * 12, st, a);
+    else launch_k(pdl, post_kernel<YF_MODE_VALIDATE>, B, POST_NT, (size_t)a.sort_cap * 12, st, a);
     ctx->launches++;
     CU(cudaGetLastError());
     return YF_OK;

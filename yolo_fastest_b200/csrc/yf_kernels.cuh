@@ -67,6 +67,12 @@ __device__ __forceinline__ void copy_f4(float* __restrict__ dst, const float* __
 
 // ---- async-proxy primitives (sm_90+/sm_100a): mbarrier, TMA tensor tiles, bulk copies ---------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Programmatic dependent launch (yf_api.cu: launch_k): a kernel launched with the programmatic-serialization attribute starts as soon as
+// every CTA of its predecessor has executed pdl_trigger() (or exited) — its set-up (barriers, TMEM allocation, weights into shared
+// memory / registers) overlaps the predecessor's tail — and must execute pdl_wait() before it touches any activation: the wait returns
+// when the predecessor grid has completed and its writes are visible. Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -955,11 +961,13 @@ pw_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __res
     const int b = blockIdx.x / tiles;
     const int p0t = (blockIdx.x - b * tiles) * C::PIXT;
     const float* xb = x + (size_t)b * C::K * HW;
+    copy_f4<NT>(Ws, wts, C::WFLOATS);
+    pdl_trigger();
+    pdl_wait();
     for (int idx = threadIdx.x; idx < C::K * C::PIXT; idx += NT) {
         const int k = idx / C::PIXT, p = idx - k * C::PIXT;
         Xs[idx] = (p0t + p < HW) ? __ldg(xb + (size_t)k * HW + p0t + p) : 0.f;
     }
-    copy_f4<NT>(Ws, wts, C::WFLOATS);
     __syncthreads();
     float acc[C::IPT][C::PN][4];
 #pragma unroll

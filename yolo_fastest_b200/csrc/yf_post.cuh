@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(POST_NT) post_kernel(const PostArgs a) {
     unsigned char* alive = a.alive + (size_t)b * a.NC;
     if (tid == 0) s_flags = 0;
     for (int c = tid; c <= a.nc; c += POST_NT) s_start[c] = 0;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // programmatic dependent launch (yf_kernels.cuh: pdl_wait): the heads are
+    asm volatile("griddepcontrol.wait;" ::: "memory");                   // the predecessor's output
     __syncthreads();
 
     // ---- phase 1: decode + confidence filter + ordered compaction -------------------------------

@@ -86,6 +86,8 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
         for (int i = 0; i < C::NS; ++i) { mbar_init(&dfull[i], NWW); mbar_init(&dfree[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&ofull[i], 1); mbar_init(&ofree[i], C::NEW); }
         mbar_fence_init();
+        mbar_expect_tx(&wres, C::WFLOATS * 4);                   // before the dependency wait: weights are not activations
+        bulk_load(Wr, wts, C::WFLOATS * 4, &wres);
     }
     if (warp == NWW + C::NEW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)C::TCOLS) : "memory");
@@ -94,6 +96,8 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem = tmem_slot;
     const int ntile = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -102,8 +106,6 @@ dense_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const float*
         if (ntile > 0 && elect_one()) {
             // instruction descriptors: A is K-major here (bit 15 clear), unlike the MN-major operands of the other kernels
             constexpr uint32_t IDESC_A = umma_idesc_tf32(C::NMAIN) & ~(1u << 15), IDESC_B = umma_idesc_tf32(32) & ~(1u << 15);
-            mbar_expect_tx(&wres, C::WFLOATS * 4);
-            bulk_load(Wr, wts, C::WFLOATS * 4, &wres);
             // A: core matrices of 8 pixels x 16 B; K-adjacent one = next channel group (2 planes further, LBO), next row group = two input rows (SBO)
             const uint64_t de0 = umma_desc(smem_u32(Ebuf), 2 * C::PLANE * 4, 2 * C::ROW * 4, 0);
             const uint64_t dw0 = umma_desc(smem_u32(Wr), 128, 256, 0);

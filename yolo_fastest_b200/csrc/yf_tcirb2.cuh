@@ -81,6 +81,8 @@ irbtc2_kernel(const float* __restrict__ x, float* __restrict__ y, const float* _
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem = tmem_slot;
     const int ntile = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 

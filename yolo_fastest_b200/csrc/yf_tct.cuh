@@ -186,6 +186,8 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
         }
         mbar_init(&dfull, C::NWORK); mbar_init(&dfree, 1);
         mbar_fence_init();
+        mbar_expect_tx(&wres, C::WRES * 4);                     // resident operands: issued before the dependency wait (weights are not activations)
+        bulk_load(Wr, wts, C::WRES * 4, &wres);
     }
     if (role == TT_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)C::TCOLS) : "memory");
@@ -197,6 +199,8 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem = tmem_slot;
     const int ntile = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int tpi = tiles_x * tiles_y;
@@ -215,8 +219,6 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
         if (ntile > 0 && elect_one()) {
             constexpr uint32_t IDESC_E = umma_idesc_tf32(C::NCH) & ~(1u << 15);          // A and B K-major
             constexpr uint32_t IDESC3A = umma_idesc_tf32(2 * C::COUTP), IDESC3B = umma_idesc_tf32(C::COUTP);
-            mbar_expect_tx(&wres, C::WRES * 4);
-            bulk_load(Wr, wts, C::WRES * 4, &wres);
             const uint64_t dw1h = umma_desc(smem_u32(Wr + C::OFF_W1H), 128, (C::KX / 4) * 128, 0);
             const uint64_t dw1l = umma_desc(smem_u32(Wr + C::OFF_W1L), 128, (C::KX / 4) * 128, 0);
             const uint64_t dxh = umma_desc(smem_u32(Xhi), 128, (C::KX / 4) * 128, 0);

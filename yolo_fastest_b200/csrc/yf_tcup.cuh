@@ -72,6 +72,8 @@ upcat_tc_kernel(const float* __restrict__ skip /*[B,136,H,W]*/, const float* __r
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem = tmem_slot;
     const int ntile = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int Hp = H / 2, Wp = W / 2;

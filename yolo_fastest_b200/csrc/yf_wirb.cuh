@@ -116,6 +116,8 @@ wirb_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y, con
         for (int m = 0; m < CMID; ++m) w2r[m] = __ldg(wts + C::OFF_W2 + pn * CMID + m);
     }
     const float* w2s = W2sh + pn * C::W2S;
+    pdl_trigger();
+    pdl_wait();                                                 // weights are in registers / shared memory: now the predecessor's output may be read
 
     // ---- this warp's units and the flat sequence of their boxes ---------------------------------------------------------------
     const int NCH = wirb_nch<C>(R);
@@ -377,6 +379,8 @@ wstem_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y, co
 #pragma unroll
     for (int t = 0; t < 9; ++t) w0x[t] = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_W0 + t * 8) + xp);
     const float2 b0x = __ldg(reinterpret_cast<const float2*>(wts + C::OFF_B0) + xp);
+    pdl_trigger();
+    pdl_wait();
 
     const int NCH = (R + 2) / RC;                               // the host picks R = NCH * RC - 2
     const int gw = blockIdx.x * C::NW + warp, tw = gridDim.x * C::NW;
