@@ -87,10 +87,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
-// 4-byte cp.async with zero fill (src_bytes = 0 writes zeros and does not touch src): halo tiles of a planar
-// [C][H][W] tensor start 1-2 floats left of a 16-byte boundary, which rules out the tensor-tile form of TMA
-// (cp.async.bulk.tensor faults on sm_100a when the innermost start coordinate is not 16-byte aligned —
-// tools/selftest/tma_selftest.cu), so tiles are staged with LDGSTS and only the weight blocks use bulk TMA.
+// 4-byte cp.async with zero fill (src_bytes = 0 writes zeros and does not touch src): the block-cooperative engine of round 1 stages
+// its halo tiles with LDGSTS (they start 1-2 floats left of a 16-byte boundary); the round-2 engines use tensor-tile TMA boxes that
+// start at the aligned column instead (yf_tma.cuh).
 __device__ __forceinline__ void cp_async4(float* dst, const float* src, int src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
