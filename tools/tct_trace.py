@@ -28,7 +28,7 @@ lib = _lib.lib()
 lib.yf_debug_trace.argtypes = [C.c_void_p, C.c_int]
 assert lib.yf_debug_trace(buf, 16 * 64) == 0
 t = [[buf[s * 16 + e] for e in range(16)] for s in range(64)]
-print("tile | worker: efull-wait  E-readout  dfree-wait  rows(FMA+stores)  - | total || mma (rel. to worker tile start): expand(t+1) at, issue; project(t) at, issue || staging of tile t (rel.): start, rawfull, xfree, put done")
+print("tile | worker: efull-wait  compute  dfree-wait  stores  epilogue | total || mma (rel. to worker tile start): expand(t+1) at, issue; project(t) at, issue || staging of tile t (rel.): start, rawfull, xfree, put done")
 for s in range(3, 24):
     w = t[s]
     if not w[0] or not t[s + 1][0]:

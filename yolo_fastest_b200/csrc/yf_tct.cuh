@@ -399,32 +399,7 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
             mbar_wait(&efull[t % C::NEB], (t / C::NEB) & 1);
             tc_fence_after();
             if (tid == 0) TT_TRACE(t, 1);
-            // One output row (8 pixels) of this thread's channel -> the project operand: ReLU, hi | lo split, two 128-bit stores each.
-            // Lanes c and c + 4 of a 128-bit store phase own the same banks (the operand's 32-byte chunks are swizzled by c & 3 only):
-            // the odd 4-channel group writes the two pixel quads of a row in the opposite order.
-            auto put_row = [&](int rr, const float (&acc)[8]) {
-                if (!cvalid) return;
-                float v[2][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float p0 = fmaxf(acc[i], 0.f), p1 = fmaxf(acc[4 + i], 0.f);
-                    v[0][i] = swp ? p1 : p0;
-                    v[1][i] = swp ? p0 : p1;
-                }
-                const int ch = (rr ^ (cl & 3)) << 3;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float hi[4], lo[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { hi[i] = tf32_hi(v[h][i]); lo[i] = v[h][i] - hi[i]; }
-                    const int o = ch + ((h ^ (int)swp) << 2);
-                    st4(dh + o, make_float4(hi[0], hi[1], hi[2], hi[3]));
-                    st4(dl + o, make_float4(lo[0], lo[1], lo[2], lo[3]));
-                }
-            };
-            // The operand buffer D is single: its stores have to wait for the project MMA of tile t - 1. That MMA was issued when the
-            // workers finished tile t - 1 and has completed by the time E of tile t has been read, so the wait sits HERE, ahead of the
-            // arithmetic, and every row is stored as soon as it is computed — the stores of row rr overlap the FMAs of row rr + 1.
+            float a[4][8];
             if (C::S == 1) {
                 float e[6][10];
 #pragma unroll
@@ -432,21 +407,16 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&efree[t % C::NEB]);
-                if (tid == 0) TT_TRACE(t, 2);
-                if (t >= 1) mbar_wait(&dfree, (t - 1) & 1);
-                if (tid == 0) TT_TRACE(t, 3);
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
-                    float a[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = bd;
+                    for (int i = 0; i < 8; ++i) a[rr][i] = bd;
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) a[i] = fmaf(w[dy * 3 + dx], e[rr + dy][i + dx], a[i]);
-                    put_row(rr, a);
+                            for (int i = 0; i < 8; ++i) a[rr][i] = fmaf(w[dy * 3 + dx], e[rr + dy][i + dx], a[rr][i]);
                 }
             } else {
                 // stride 2: output row rr reads input rows 2 rr .. 2 rr + 2 (17 columns each); three rows live at a time, row r in slot r % 3
@@ -454,9 +424,6 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
                 tmem_ld_row17(te, e[0]);
                 int sb = 0, soy0 = 0, sox0 = 0;
                 if (C::SKIP) origin(t, sb, soy0, sox0);
-                if (tid == 0) TT_TRACE(t, 2);
-                if (t >= 1) mbar_wait(&dfree, (t - 1) & 1);
-                if (tid == 0) TT_TRACE(t, 3);
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                     tmem_ld_row17(te + (2 * rr + 1) * C::HW, e[(2 * rr + 1) % 3]);
@@ -481,16 +448,42 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&efree[t % C::NEB]);
                     }
-                    float a[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = bd;
+                    for (int i = 0; i < 8; ++i) a[rr][i] = bd;
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) a[i] = fmaf(w[dy * 3 + dx], e[(2 * rr + dy) % 3][2 * i + dx], a[i]);
-                    put_row(rr, a);
+                            for (int i = 0; i < 8; ++i) a[rr][i] = fmaf(w[dy * 3 + dx], e[(2 * rr + dy) % 3][2 * i + dx], a[rr][i]);
+                }
+            }
+            // everything above overlapped the project MMA of tile t - 1; only the operand stores have to wait for it
+            if (tid == 0) TT_TRACE(t, 2);
+            if (t >= 1) mbar_wait(&dfree, (t - 1) & 1);
+            if (tid == 0) TT_TRACE(t, 3);
+            if (cvalid) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    // Lanes c and c + 4 of a 128-bit store phase own the same banks (the operand's 32-byte chunks are swizzled by c & 3
+                    // only): the odd 4-channel group writes the two pixel quads of a row in the opposite order.
+                    float v[2][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float p0 = fmaxf(a[rr][i], 0.f), p1 = fmaxf(a[rr][4 + i], 0.f);
+                        v[0][i] = swp ? p1 : p0;
+                        v[1][i] = swp ? p0 : p1;
+                    }
+                    const int ch = (rr ^ (cl & 3)) << 3;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { hi[i] = tf32_hi(v[h][i]); lo[i] = v[h][i] - hi[i]; }
+                        const int o = ch + ((h ^ (int)swp) << 2);
+                        st4(dh + o, make_float4(hi[0], hi[1], hi[2], hi[3]));
+                        st4(dl + o, make_float4(lo[0], lo[1], lo[2], lo[3]));
+                    }
                 }
             }
             fence_proxy_async();
