@@ -28,12 +28,12 @@ lib = _lib.lib()
 lib.yf_debug_trace.argtypes = [C.c_void_p, C.c_int]
 assert lib.yf_debug_trace(buf, 16 * 64) == 0
 t = [[buf[s * 16 + e] for e in range(16)] for s in range(64)]
-print("tile | worker: efull-wait  compute  dfree-wait  stores  epilogue | total || mma (rel. to worker tile start): expand(t+1) at, issue; project(t) at, issue || staging of tile t (rel.): start, rawfull, xfree, put done")
+print("tile | worker: efull-wait  compute  dfree-wait  stores  fence+arrive | total || mma (rel. to worker tile start): expand(t+1) at, issue; project(t) at, issue || staging of tile t (rel.): start, rawfull, xfree, put done")
 for s in range(3, 24):
     w = t[s]
     if not w[0] or not t[s + 1][0]:
         break
     o = w[0]
     print("%4d | %10d %8d %10d %8d %8d | %6d || %6d %6d %6d %6d || %6d %6d %6d %6d" % (
-        s, w[1] - w[0], w[2] - w[1], w[3] - w[2], w[4] - w[3], w[5] - w[4], t[s + 1][0] - w[0],
+        s, w[1] - w[0], w[2] - w[1], w[3] - w[2], w[5] - w[3], w[4] - w[5], t[s + 1][0] - w[0],
         w[6] - o, w[7] - w[6], w[8] - o, w[9] - w[8], w[10] - o, w[11] - o, w[12] - o, w[13] - o))

@@ -486,6 +486,7 @@ irbt_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ 
                     }
                 }
             }
+            if (tid == 0) TT_TRACE(t, 5);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&dfull);
