@@ -23,6 +23,7 @@
 #include "yf_tcup.cuh"
 #include "yf_tcirb2.cuh"
 #include "yf_tcdense.cuh"
+#include "yf_tcdense2.cuh"
 #include "yf_prep.cuh"
 
 using namespace yf;
@@ -131,6 +132,7 @@ struct GroupArgs {
     float* skip = nullptr;       // dual output
     const float* w = nullptr;    // packed weights (device)
     const float* w2 = nullptr;   // second weight block of the same group (the channel-lane kernel's, where a group keeps two engines)
+    const DenseSmall* small = nullptr;   // the dense group's small weights (host copy in the ctx: passed to the kernel by value)
     bool pdl = false;            // launch with programmatic stream serialization (set per launch by forward_impl; kernels with pdl_wait() only)
     int Hin = 0, Win = 0, Hout = 0, Wout = 0;
     int headn = 0;
@@ -193,6 +195,7 @@ struct yf_ctx {
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_back = nullptr;      // H2D of inputs / kernels / D2H of results
     cudaStream_t s_cap = nullptr;                       // graphs are captured here (the caller's stream may be the legacy stream, which cannot capture)
     cudaStream_t s_side = nullptr;                      // small batches: the head_5 branch runs here, beside the upsample branch
+    DenseSmall dense_small;                             // conv1_8 / conv2_1 weights and the biases of the dense group (kernel parameter of dense_ta_kernel)
     bool last_forward_forked = false;                   // the last forward ended with an event join: the head kernel is launched the ordinary way
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned char* sl_u8[2] = {nullptr, nullptr};
@@ -634,6 +637,24 @@ void launch_dense_tc(const GroupArgs& g, const void*, bool, int B, cudaStream_t 
     const int total = B * tx * ty;
     const int grid = total < g.resident ? total : g.resident;
     launch_k(g.pdl, dense_tc_kernel<C>, grid, C::NT, C::SMEM_BYTES, st, g.x, g.y, g.w, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
+}
+// the same group with the A operand in tensor memory (yf_tcdense2.cuh); same packed weights
+#ifndef YF_DENSE_TA
+#define YF_DENSE_TA 1
+#endif
+int occ_dense_ta() { return occ_of(dense_ta_kernel<DenseTaCfg>, DenseTaCfg::NT, DenseTaCfg::SMEM_BYTES); }
+void launch_dense_ta(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
+    using C = DenseTaCfg;
+    TmaCache* tc = g.tc;
+    if (tc->ptr != g.x || tc->B != B) {
+        tc->failed = tma_make_map4(&tc->map, g.x, 4, B, 4, g.Hin, g.Win, C::XW, C::RH, 4) != 0;
+        tc->ptr = g.x; tc->B = B;
+    }
+    if (tc->failed) return;
+    const int tx = cdiv(g.Wout, C::TW), ty = cdiv(g.Hout, C::TH);
+    const int total = B * tx * ty;
+    const int grid = total < g.resident ? total : g.resident;
+    launch_k(g.pdl, dense_ta_kernel<C>, grid, C::NT, C::SMEM_BYTES, st, tc->map, g.y, g.w, *g.small, g.Hin, g.Win, g.Hout, g.Wout, tx, ty, total);
 }
 void launch_dense(const GroupArgs& g, const void*, bool, int B, cudaStream_t st) {
     using C = CfgDense;
@@ -1222,7 +1243,11 @@ static void build_plan(yf_ctx* ctx) {
     chain(make_irb<CfgRes1>("res1_1", 4), 2, 2);
 #endif
 #if YF_DENSE_TC
-    { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense_tc; g.occupancy = &occ_dense_tc; g.out_ch = 8; chain(g, 2, 4); }
+    {
+        Group g{}; g.name = "conv2_1"; g.launch = &launch_dense_tc; g.occupancy = &occ_dense_tc; g.out_ch = 8;
+        if (YF_DENSE_TA) { g.launch = &launch_dense_ta; g.occupancy = &occ_dense_ta; g.a.small = &ctx->dense_small; }
+        chain(g, 2, 4);
+    }
 #else
     { Group g{}; g.name = "conv2_1"; g.launch = &launch_dense; g.occupancy = &occ_dense; g.out_ch = 8; chain(g, 2, 4); }
 #endif
@@ -1377,6 +1402,7 @@ extern "C" int yf_create_variant(yf_ctx** out, int device, int in_ch, int num_cl
         cudaFuncSetAttribute(stem_kernel<CfgStem3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgStem3::SMEM_BYTES),
         cudaFuncSetAttribute(dense_kernel<CfgDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDense::SMEM_BYTES),
         cudaFuncSetAttribute(dense_tc_kernel<CfgDenseTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgDenseTc::SMEM_BYTES),
+        cudaFuncSetAttribute(dense_ta_kernel<DenseTaCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseTaCfg::SMEM_BYTES),
         cudaFuncSetAttribute(pw_kernel<CfgPw52>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPw52::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_kernel<CfgUpCat>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCat::SMEM_BYTES),
         cudaFuncSetAttribute(upcat_tc_kernel<CfgUpCatTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgUpCatTc::SMEM_BYTES),
@@ -1451,6 +1477,15 @@ extern "C" int yf_load_weights(yf_ctx* ctx, const float* host_blob, int64_t n_fl
     res(CfgRes1{}, "res1_1");
 #endif
     offs.push_back(YF_DENSE_TC ? pack_dense_tc(P, f) : pack_dense(P, f));
+    {
+        DenseSmall& d = ctx->dense_small;
+        for (int c = 0; c < 24; ++c) {
+            for (int k = 0; k < 4; ++k) d.w8[k][c] = f.w("conv1_8")[c * 4 + k];
+            d.b8[c] = f.b("conv1_8")[c]; d.b9[c] = f.b("conv1_9")[c];
+            for (int j = 0; j < 8; ++j) d.w21[c][j] = f.w("conv2_1")[j * 24 + c];
+        }
+        for (int j = 0; j < 8; ++j) d.b21[j] = f.b("conv2_1")[j];
+    }
 #if YF_USE_WIRB
     offs.push_back(pack_wirb<CfgRes2W>(P, f, "res2_1.conv1", "res2_1.conv2", "res2_1.conv3"));
     offs.push_back(pack_wirb<CfgRes2W>(P, f, "res2_2.conv1", "res2_2.conv2", "res2_2.conv3"));
