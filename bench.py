@@ -452,7 +452,7 @@ def main():
                     "tf32_peak": tf32_peak, "executed_TFLOP/s": round(3 * top["TFLOP/s"], 1), "frac_of_tf32_executed": top.get("tf32_frac_executed"),
                     "tensor_pipe_util_ncu": top.get("ncu", {}).get("tensor_pipe_pct"),
                     "hbm_GB/s": top["GB/s"], "hbm_frac": top["hbm_frac"],
-                    "note": "fp32 parity needs 3xTF32 (hi*hi + hi*lo + lo*hi): algorithmic FLOPs are a third of the executed tensor FLOPs; the MMAs of a tile need 1.08 k of its 4.9 k cycles at the tcgen05 dispatch floor - the kernel is bound by shared-memory bandwidth (the implicit GEMM re-reads the E operand once per tap: ~300 KB of operand reads + 108 KB of producer stores per 128-pixel tile, profiles/r02_dense_phase_trace.txt)"}
+                    "note": "fp32 parity needs 3xTF32 (hi*hi + hi*lo + lo*hi): algorithmic FLOPs are a third of the executed tensor FLOPs; the MMAs of a 128-pixel tile need 1.08 k of its ~4.4 k cycles at the tcgen05 dispatch floor. A operand in tensor memory (dense_ta_kernel): no activation passes through shared memory; the kernel is bound by the CUDA-core instructions of its producer warps (conv1_8 + ReLU + hi/lo split, recomputed 2.25x; ncu: issue slots 66%, ALU pipe 50%, tensor pipe 25%)"}
     else:
         roofline = {"bound": top["bound"], "achieved": top["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": top["hbm_frac"], "traffic": traffic,
                     "traffic_source": traffic_source, "kernel": top["name"], "share_of_forward": top["share"], "peak_source": peak_src}

@@ -1,4 +1,4 @@
-"""Phase trace of dense_tc_kernel (library built with -DYF_TC_TRACE -DYF_DENSE_TRACE -DYF_TC_TRACE_CMID=1): per tile of CTA 0, cycles
+"""Phase trace of dense_ta_kernel / dense_tc_kernel (-DYF_DENSE_TA=0) (library built with -DYF_TC_TRACE -DYF_DENSE_TRACE -DYF_TC_TRACE_CMID=1): per tile of CTA 0, cycles
 between the boundaries of worker thread 0 and of the tensor-core thread."""
 import ctypes as C
 import os

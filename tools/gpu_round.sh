@@ -17,7 +17,7 @@ echo "bench 256 exit $?" >> gpurun_out/summary.txt
 timeout 600 python bench.py --batch 1 --steps 200 --warmup 20 --no-cpu-baseline > gpurun_out/bench_b1.log 2> gpurun_out/bench_b1.err
 echo "bench b1 exit $?" >> gpurun_out/summary.txt
 # every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
-K='regex:irb_kernel|irbt_kernel|irbtc_kernel|irbtc2_kernel|dwpw_tc_kernel|dense_tc_kernel|stem_kernel|wstem_kernel|wirb_kernel|upcat_kernel|upcat_tc_kernel|pw_kernel|post_kernel|compact_dets_kernel'
+K='regex:irb_kernel|irbt_kernel|irbtc_kernel|irbtc2_kernel|dwpw_tc_kernel|dense_tc_kernel|dense_ta_kernel|stem_kernel|wstem_kernel|wirb_kernel|upcat_kernel|upcat_tc_kernel|pw_kernel|post_kernel|compact_dets_kernel'
 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
   timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1

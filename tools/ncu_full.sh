@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu --set full over the 30 library kernels of ONE forward at batch 256 (the headline workload), after a plain run of the same command.
 # The report itself stays on the box (size). Back in gpurun_out/: the raw CSV page, the one-line-per-kernel summary, and profiles-ready r02_ncu_metrics.json.
-K='regex:irb_kernel|irbt_kernel|irbtc_kernel|irbtc2_kernel|dwpw_tc_kernel|dense_tc_kernel|stem_kernel|wstem_kernel|wirb_kernel|upcat_kernel|upcat_tc_kernel|pw_kernel|pwpw_kernel'
+K='regex:irb_kernel|irbt_kernel|irbtc_kernel|irbtc2_kernel|dwpw_tc_kernel|dense_tc_kernel|dense_ta_kernel|stem_kernel|wstem_kernel|wirb_kernel|upcat_kernel|upcat_tc_kernel|pw_kernel|pwpw_kernel'
 CMD="python tools/profile_groups.py 512x640 256"
 mkdir -p gpurun_out
 timeout 600 $CMD > gpurun_out/full_plain.log 2>&1 && \

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "yolo_fastest_b200", "libyf_b200.so")
 outdir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
 KEYS = ["UTMALDG", "UBLKCP", "UTCHMMA", "LDTM", "FFMA2", "FFMA", "LDGSTS", "SYNCS", "LDS", "STS", "BAR"]
-FAMILIES = {"wirb": ["wirb_kernel", "wstem_kernel"], "tcgen05": ["irbt_kernel", "irbtc_kernel", "irbtc2_kernel", "dwpw_tc_kernel", "upcat_tc_kernel", "dense_tc_kernel"],
+FAMILIES = {"wirb": ["wirb_kernel", "wstem_kernel"], "tcgen05": ["irbt_kernel", "irbtc_kernel", "irbtc2_kernel", "dwpw_tc_kernel", "upcat_tc_kernel", "dense_tc_kernel", "dense_ta_kernel"],
             "ffma": ["irb_kernel", "pw_kernel", "pwpw_kernel", "stem_kernel", "upcat_kernel"], "post": ["post_kernel", "compact_dets_kernel", "prep_bgr"]}
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 funcs, cur = collections.OrderedDict(), None
