@@ -43,3 +43,22 @@ def test_oracle_matches_live_cv2():
     for v in (0, 255):
         frame = np.full((50, 70, 3), v, np.uint8)
         assert np.array_equal(po.pre_process(frame, 32, 64), cv2.resize(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY), (64, 32)))
+
+
+def test_u8_normalisation_without_table_is_the_reference_division():
+    """yf_wirb.cuh: norm_u8 computes (b - 128) / 255 as q + (n - 255 q) * r with r = fl(1 / 255): for every byte the result is the
+    correctly rounded fp32 quotient, i.e. exactly what the reference's `(img - 128.0) / 255.0` gives (detect.py:124).  Checked in exact
+    rational arithmetic: no floating-point emulation of the fused multiply-adds is trusted."""
+    from fractions import Fraction as F
+    r = np.float32(1.0) / np.float32(255.0)
+    for b in range(256):
+        n = np.float32(b) - np.float32(128.0)
+        ref = np.float32(n / np.float32(255.0))
+        q = np.float32(n * r)
+        res_exact = F(float(n)) - 255 * F(float(q))                    # fmaf(-255, q, n) before rounding
+        res = np.float32(float(res_exact))
+        assert F(float(res)) == res_exact                              # the residual is exactly representable
+        x = F(float(q)) + F(float(res)) * F(float(r))                  # the value the last fmaf rounds
+        lo, hi = np.nextafter(ref, np.float32(-np.inf)), np.nextafter(ref, np.float32(np.inf))
+        d = abs(x - F(float(ref)))
+        assert d < abs(x - F(float(lo))) and d < abs(x - F(float(hi))), b

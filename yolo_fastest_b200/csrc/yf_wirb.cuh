@@ -26,6 +26,17 @@
 
 namespace yf {
 
+// (b - 128) / 255 of byte K of `word`, bit for bit the reference's fp32 division (detect.py:124), without a table: the byte goes into the
+// mantissa of 2^23 (one PRMT), n = b - 128 exactly, q = n * (1 / 255) is within one ulp, and one residual step q + (n - 255 q) * (1 / 255)
+// rounds correctly — checked exhaustively for the 256 byte values in exact rational arithmetic (tests/test_preprocess_cpu.py).
+template <int K>
+__device__ __forceinline__ float norm_u8(uint32_t word) {
+    const float n = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | K)) - 8388736.0f;
+    const float r = 1.0f / 255.0f;
+    const float q = __fmul_rn(n, r);
+    return __fmaf_rn(__fmaf_rn(-255.0f, q, n), r, q);
+}
+
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 fma2s(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
 __device__ __forceinline__ float2 mul2s(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
@@ -328,7 +339,7 @@ struct WstemCfg {
     static constexpr int OFF_W0 = 0, OFF_B0 = 72, OFF_W1 = 80, OFF_B1 = 144, OFF_WD = 152, OFF_BD = 224, OFF_W2 = 232, OFF_B2 = 264;
     static constexpr int WFLOATS = 268;
     template <bool U8> __host__ __device__ static constexpr int warp_bytes() { return (U8 ? 2 * RAWU + RAWF * 4 : 2 * RAWF * 4) + 2 * C0F * 4 + 2 * DROW * 4; }
-    template <bool U8> __host__ __device__ static constexpr int smem_bytes() { return NW * warp_bytes<U8>() + (U8 ? 1024 : 0) + 128; }
+    template <bool U8> __host__ __device__ static constexpr int smem_bytes() { return NW * warp_bytes<U8>() + 128; }
     static_assert(smem_bytes<false>() <= 227 * 1024 && smem_bytes<true>() <= 227 * 1024, "does not fit shared memory");
 };
 
@@ -346,11 +357,8 @@ wstem_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y, co
     float* Rf = reinterpret_cast<float*>(wb + (U8 ? 2 * C::RAWU : 0));          // fp32 raw rows: U8 one normalised copy, else two boxes
     float* C0b = Rf + (U8 ? 1 : 2) * C::RAWF;                                   // two conv0 row buffers
     float* Db = C0b + 2 * C::C0F;
-    float* Lut = reinterpret_cast<float*>(base + (size_t)C::NW * C::template warp_bytes<U8>());
     if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); }
     if (threadIdx.x == 0) tma_prefetch_desc(&xmap);
-    if (U8)
-        for (int i = threadIdx.x; i < 256; i += C::NW * 32) Lut[i] = ((float)i - 128.0f) / 255.0f;
     mbar_fence_init();
     __syncthreads();
 
@@ -456,7 +464,7 @@ wstem_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y, co
                     const int row = i / (C::RAWW / 4), q4 = i - row * (C::RAWW / 4);
                     const uint32_t v = *reinterpret_cast<const uint32_t*>(ub8 + row * C::RAWWU + 12 + 4 * q4);
                     const bool in = (unsigned)(ry + row) < (unsigned)Hin && (unsigned)(rx + 4 * q4) < (unsigned)Win;
-                    st4(Rf + row * C::RAWW + 4 * q4, in ? make_float4(Lut[v & 255], Lut[(v >> 8) & 255], Lut[(v >> 16) & 255], Lut[v >> 24])
+                    st4(Rf + row * C::RAWW + 4 * q4, in ? make_float4(norm_u8<0>(v), norm_u8<1>(v), norm_u8<2>(v), norm_u8<3>(v))
                                                         : make_float4(0.f, 0.f, 0.f, 0.f));
                 }
                 __syncwarp();
