@@ -55,7 +55,8 @@ __device__ __forceinline__ void tmem_ld24(uint32_t taddr, float (&v)[24]) {
     for (int i = 0; i < 24; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// NSPLIT = 1: 12 producer warps (8 channels per thread, tap and step); 2: 24 warps, each half of the step's channels
+// NSPLIT = 1: 12 producer warps (8 channels per thread, tap and step); 2: 24 warps, each half of the step's channels (measured
+// slower, 0.784 against 0.668 ms: the kernel is bound by instruction issue, not by latency — kept as the A/B switch YF_DENSE_TA_SPLIT)
 template <int NSPLIT_ = 1>
 struct DenseTaCfgT {
     static constexpr int NSPLIT = NSPLIT_, CPT = 8 / NSPLIT;
