@@ -74,3 +74,20 @@ def test_create_rejects_bad_arguments():
     assert l.yf_create(None, 0, 1, 3, 3, 1, 256, 320) == -1
     assert l.yf_forward(None, None, 1, None, None, None) == -1
     assert l.yf_launch_count(None) == -1
+
+
+def test_build_is_content_addressed_and_idempotent():
+    """build() decides by a hash of the sources recorded beside each library, not by mtimes (a copy of the tree to the GPU box does not
+    keep them in order — N ranks rebuilding the same .so at once was the failure mode), holds a file lock while it compiles and renames
+    the result into place."""
+    import os
+    import __graft_entry__ as g
+    g.build()
+    sources = [os.path.join(g.CSRC, f) for f in sorted(os.listdir(g.CSRC)) if f.endswith((".cu", ".cuh"))]
+    sources.append(os.path.join(g.ROOT, "include", "yf.h"))
+    assert not g._stale(g.LIB, sources, g.NVCC_FLAGS)
+    before = os.path.getmtime(g.LIB)
+    os.utime(sources[0], None)                       # a newer mtime alone must not trigger a rebuild
+    g.build()
+    assert os.path.getmtime(g.LIB) == before
+    assert g._stale(g.LIB, sources, g.NVCC_FLAGS + ["-DSOMETHING_ELSE"])
