@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "yolo_fastest_b200", "libyf_b200.so")
 outdir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
-KEYS = ["UTMALDG", "UBLKCP", "UTCHMMA", "LDTM", "FFMA2", "FFMA", "LDGSTS", "SYNCS", "LDS", "STS", "BAR"]
+KEYS = ["UTMALDG", "UBLKCP", "UTCHMMA", "LDTM", "STTM", "FFMA2", "FFMA", "LDGSTS", "SYNCS", "LDS", "STS", "BAR"]
 FAMILIES = {"wirb": ["wirb_kernel", "wstem_kernel"], "tcgen05": ["irbt_kernel", "irbtc_kernel", "irbtc2_kernel", "dwpw_tc_kernel", "upcat_tc_kernel", "dense_tc_kernel", "dense_ta_kernel"],
             "ffma": ["irb_kernel", "pw_kernel", "pwpw_kernel", "stem_kernel", "upcat_kernel"], "post": ["post_kernel", "compact_dets_kernel", "prep_bgr"]}
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
@@ -35,7 +35,7 @@ for fam, pats in FAMILIES.items():
             ops[op.split(".")[0]] += 1
         out.append("%s" % name.replace("yf::", "")[:200])
         out.append("  %d instructions: " % len(ins) + " ".join("%s %d" % (k, ops[k]) for k in KEYS if ops[k]))
-        for k in ("UTMALDG", "UTCHMMA", "LDTM", "UBLKCP", "FFMA2"):
+        for k in ("UTMALDG", "UTCHMMA", "LDTM", "STTM", "UBLKCP", "FFMA2"):
             ex = [l for l in ins if re.search(r"\b%s\b" % k, l.split(";")[0])][:2]
             out += ["    " + e[:150] for e in ex]
         out.append("")
