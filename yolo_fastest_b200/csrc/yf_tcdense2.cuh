@@ -31,6 +31,11 @@ __device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, u
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
                  ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// (r0, r1) = (a0, a1) + (b0, b1) in one issue slot (add.rn.f32x2), bit-identical to two scalar adds
+__device__ __forceinline__ void add2(float a0, float a1, float b0, float b1, float& r0, float& r1) {
+    const float2 r = __fadd2_rn(make_float2(a0, a1), make_float2(b0, b1));
+    r0 = r.x; r1 = r.y;
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
@@ -179,14 +184,14 @@ dense_ta_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y,
                 float v[24], t24[24];
                 tmem_ld24(ta + 3 * C::NMAIN, t24);                                   // the tile's lo . hi correction accumulator
 #pragma unroll
-                for (int n = 0; n < 24; ++n) v[n] = t24[n] + sw.b9[n];
+                for (int n = 0; n < 24; n += 2) add2(t24[n], t24[n + 1], sw.b9[n], sw.b9[n + 1], v[n], v[n + 1]);
 #pragma unroll
                 for (int cb = 0; cb < 3; ++cb) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {                                    // columns [0, 24) E_hi . W9hi, [24, 48) E_hi . W9lo
                         tmem_ld24(ta + cb * C::NMAIN + h * 24, t24);
 #pragma unroll
-                        for (int n = 0; n < 24; ++n) v[n] += t24[n];
+                        for (int n = 0; n < 24; n += 2) add2(v[n], v[n + 1], t24[n], t24[n + 1], v[n], v[n + 1]);
                     }
                 }
                 tc_fence_before();
@@ -200,7 +205,7 @@ dense_ta_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y,
                 for (int n = 0; n < 24; ++n) {
                     const float vn = fmaxf(v[n], 0.f);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) ps[j] = fmaf(sw.w21[n][j], vn, ps[j]);
+                    for (int j = 0; j < 8; j += 2) ffma2(sw.w21[n][j], sw.w21[n][j + 1], vn, ps[j], ps[j + 1]);
                 }
                 const int gy = ey0 + eoy, gx = ex0 + eox;
                 if (gy < Hout && gx < Wout) {
@@ -273,7 +278,8 @@ dense_ta_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y,
                                     for (int k = 0; k < 4; ++k) ffma2(sw.w8[k][c], sw.w8[k][c + 1], xv[kx][k], e0, e1);   // k ascending, fmaf rounding per lane
                                     e0 = fmaxf(e0, 0.f); e1 = fmaxf(e1, 0.f);
                                     hi[i] = tf32_hi(e0); hi[i + 1] = tf32_hi(e1);
-                                    lo[i] = e0 - hi[i]; lo[i + 1] = e1 - hi[i + 1];
+                                    lo[i] = e0; lo[i + 1] = e1;
+                                    ffma2(hi[i], hi[i + 1], -1.f, lo[i], lo[i + 1]);     // lo = e - hi, exact either way
                                 }
                             };
                             if (C::NSPLIT == 1 || half == 0) pairs(std::integral_constant<int, 0>{});
