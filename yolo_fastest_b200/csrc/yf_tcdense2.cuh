@@ -119,10 +119,11 @@ dense_ta_kernel(const __grid_constant__ CUtensorMap xmap, float* __restrict__ y,
 
     const int tpi = tiles_x * tiles_y;
     const uint32_t inv_tx = (65536u + (uint32_t)tiles_x - 1u) / (uint32_t)tiles_x;
-    const uint32_t inv_tpi = (uint32_t)((0x100000000ull + (uint64_t)tpi - 1ull) / (uint64_t)tpi);      // tile / tpi as one multiply (tiles < 2^22)
+    const uint32_t inv_tpi = (uint32_t)((0x100000000ull + (uint64_t)tpi - 1ull) / (uint64_t)tpi);      // tile / tpi as one multiply + fix-up
     auto origin = [&](int ti, int& b, int& oy0, int& ox0) {
         const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
         b = (int)__umulhi((uint32_t)tile, inv_tpi);
+        if (b * tpi > tile) --b;                                 // the rounded-up reciprocal can overshoot by one once tile * tpi >= 2^32
         const int t = tile - b * tpi;
         const int ty = (int)(((uint32_t)t * inv_tx) >> 16);
         oy0 = ty * C::TH; ox0 = (t - ty * tiles_x) * C::TW;
